@@ -1,0 +1,288 @@
+// OptimalControlProblem implementation, CUDA_SQP path only.
+// Reference behaviour kept (src/OptimalControlProblem.cpp):
+//   * mandatory solver_settings keys (:54-62) and what is read from them (:21-32);
+//     the README spellings SQP_step / ADMM_step (readme.md:55-62) are accepted as
+//     aliases of SQP_settings.alpha / SQP_settings.step_num;
+//   * equality constraints are lhs - rhs in [0, 0] (:466-481), inequality constraints keep
+//     the caller's bounds (:448-464), vector costs are sum_i w_i e_i^2 (:574-600);
+//   * computeOptimalTrajectory pins the WHOLE first frame through lbx = ubx = frame
+//     (:93-96) and passes `reference` as p; x0 is built and validated but the SQP driver
+//     ignores it and continues from its own previous iterate (:101-113, SQP :215);
+//   * every failure surfaces as std::runtime_error("Optimization failed: ...") (:219-221).
+#include "optimal_control_problem/OptimalControlProblem.h"
+
+#include <unistd.h>
+
+#include <cstdlib>
+#include <filesystem>
+
+using casadi::DM;
+using casadi::SX;
+
+OptimalControlProblem::OptimalControlProblem(YAML::Node configNode) {
+  try {
+    if (!validateConfig(configNode)) throw std::runtime_error("Invalid configuration file");
+    if (const char* share = std::getenv("OCP_B200_SHARE_DIR")) packagePath_ = share;
+    else packagePath_ = (std::filesystem::current_path() / "ocp_b200_share").string();
+    OCPConfigPtr_ = std::make_unique<OCPConfig>(configNode);
+    configNode_ = configNode;
+
+    const YAML::Node s = configNode["solver_settings"];
+    solverSettings.maxIter = s["max_iter"].as<int>();
+    solverSettings.warmStart = s["warm_start"].as<bool>();
+    solverSettings.SQP_settings.alpha = s["SQP_settings"]["alpha"].as<double>();
+    solverSettings.SQP_settings.stepNum = s["SQP_settings"]["step_num"].as<int>();
+    if (s["SQP_step"]) solverSettings.SQP_settings.alpha = s["SQP_step"].as<double>();
+    if (s["ADMM_step"]) solverSettings.SQP_settings.stepNum = s["ADMM_step"].as<int>();
+    solverSettings.verbose = s["verbose"].as<bool>();
+    solverSettings.genCode = s["gen_code"].as<bool>();
+    solverSettings.loadLib = s["load_lib"].as<bool>();
+    if (s["recompile"]) solverSettings.recompile = s["recompile"].as<bool>();
+
+    const std::string method = s["solve_method"].as<std::string>();
+    if (method == "CUDA_SQP") {
+      setSolverType(SolverSettings::SolverType::CUDA_SQP);
+    } else if (method == "IPOPT" || method == "SQP" || method == "MIXED") {
+      throw std::invalid_argument("solve_method " + method +
+                                  " is a CasADi nlpsol plugin path and is not part of this build; use CUDA_SQP");
+    } else {
+      throw std::invalid_argument("Unknown solver type: " + method);
+    }
+    if (solverSettings.verbose) {
+      std::cout << "stage libraries are cached under: " << packagePath_ << "/code_gen" << std::endl;
+    }
+  } catch (const YAML::Exception& e) {
+    throw std::runtime_error("Error parsing YAML configuration: " + std::string(e.what()));
+  }
+}
+
+bool OptimalControlProblem::validateConfig(const YAML::Node& config) {
+  if (!config["solver_settings"]) return false;
+  const YAML::Node s = config["solver_settings"];
+  const bool sqp = (s["SQP_settings"] && s["SQP_settings"]["alpha"] && s["SQP_settings"]["step_num"]);
+  return s["max_iter"] && s["warm_start"] && sqp && s["verbose"] && s["gen_code"] && s["load_lib"] &&
+         s["solve_method"];
+}
+
+bool OptimalControlProblem::checkDirectoryPermissions(const std::string& path) {
+  try {
+    std::filesystem::path dir(path);
+    if (!std::filesystem::exists(dir)) return std::filesystem::create_directories(dir);
+    return access(path.c_str(), W_OK) == 0;
+  } catch (const std::filesystem::filesystem_error&) {
+    return false;
+  }
+}
+
+casadi::SXDict OptimalControlProblem::getNlp() {
+  SX vars = OCPConfigPtr_->getVariables();
+  if (vars.is_empty()) throw std::runtime_error("Status or input variables are empty");
+  SX constraints = SX::vertcat(getConstraints());
+  if (constraints.is_empty()) throw std::runtime_error("Constraints are empty");
+  return {{"x", vars}, {"f", getCostFunction()}, {"g", constraints}, {"p", reference_}};
+}
+
+void OptimalControlProblem::genSolver() {
+  casadi::SXDict nlp = getNlp();
+  const std::string codeDir = std::filesystem::absolute(packagePath_ + "/code_gen").string();
+  if (!checkDirectoryPermissions(codeDir))
+    throw std::runtime_error("Cannot create or write to code generation directory: " + codeDir);
+  try {
+    casadi::Dict opts;
+    opts["qpsol"] = "cuda_sqp";
+    opts["max_iter"] = solverSettings.SQP_settings.stepNum;
+    opts["alpha"] = solverSettings.SQP_settings.alpha;
+    opts["verbose"] = solverSettings.verbose ? 1 : 0;
+    opts["jit"] = false;
+    opts["code_dir"] = codeDir;
+    opts["name"] = problemName_;
+    opts["nf"] = OCPConfigPtr_->getFrameSize();
+    opts["horizon"] = OCPConfigPtr_->getHorizon();
+    OSQPSolverPtr_ = std::make_shared<SQPOptimizationSolver>(nlp, opts);
+
+    if (solverSettings.genCode) {
+      // the reference serialises localSystemFunction here (:403-425)
+      const std::string target = codeDir + "/localSystemFunction.casadi";
+      OSQPSolverPtr_->getSXLocalSystemFunction().save(target);
+      if (solverSettings.verbose) std::cout << "LocalSystemFunction saved to: " << target << std::endl;
+    }
+    if (solverSettings.verbose) {
+      std::cout << "Problem dimensions:\nVariables: " << nlp["x"].size1() << "\nConstraints: "
+                << nlp["g"].size1() << "\nParameters: " << reference_.size1() << std::endl;
+    }
+  } catch (const std::exception& e) {
+    throw std::runtime_error("Failed to generate solver: " + std::string(e.what()));
+  }
+}
+
+casadi::DMDict OptimalControlProblem::buildSolverArguments(const DM& frame, const DM& reference) {
+  const int nf = OCPConfigPtr_->getFrameSize();
+  if (frame.size1() != nf)
+    throw std::invalid_argument("State dimension mismatch: received " + std::to_string(frame.size1()) +
+                                ", expected " + std::to_string(nf));
+  if (reference.size1() != reference_.size1())
+    throw std::invalid_argument("Reference dimension mismatch: received " + std::to_string(reference.size1()) +
+                                ", expected " + std::to_string(reference_.size1()));
+  casadi::DMDict arg;
+  DM lbx = DM::vertcat(OCPConfigPtr_->getLowerBounds());
+  DM ubx = DM::vertcat(OCPConfigPtr_->getUpperBounds());
+  lbx(casadi::Slice(0, nf)) = frame;
+  ubx(casadi::Slice(0, nf)) = frame;
+  arg["lbx"] = lbx;
+  arg["ubx"] = ubx;
+  arg["lbg"] = DM::vertcat(getConstraintLowerBounds());
+  arg["ubg"] = DM::vertcat(getConstraintUpperBounds());
+  DM guess = setInitialGuess_ ? OCPConfigPtr_->getInitialGuess()
+                              : DM::repmat(DM::zeros(nf, 1), OCPConfigPtr_->getHorizon());
+  arg["x0"] = firstTime_ ? guess : optimalTrajectory_;
+  arg["p"] = reference;
+  return arg;
+}
+
+void OptimalControlProblem::computeOptimalTrajectory(const DM& frame, const DM& reference) {
+  casadi::DMDict arg = buildSolverArguments(frame, reference);
+  if (!solverInputCheck(arg)) throw std::runtime_error("Solver input validation failed");
+  try {
+    if (!OSQPSolverPtr_) throw std::runtime_error("genSolver() has not been called");
+    casadi::DMDict res = OSQPSolverPtr_->getOptimalSolution(arg);
+    firstTime_ = false;
+    if (res.empty()) throw std::runtime_error("Solver returned empty result");
+    optimalTrajectory_ = res.at("x");
+    if (solverSettings.verbose) {
+      std::cout << "\n=================== result ===================" << std::endl;
+      std::cout << "objective: " << res.at("f") << std::endl;
+      std::cout << "solution: " << res.at("x") << std::endl;
+    }
+  } catch (const std::exception& e) {
+    throw std::runtime_error("Optimization failed: " + std::string(e.what()));
+  }
+}
+
+const std::vector<double>& OptimalControlProblem::computeOptimalTrajectoryBatch(
+    int B, const std::vector<double>& frames, const std::vector<double>& references) {
+  const int nf = OCPConfigPtr_->getFrameSize();
+  const int N = nf * OCPConfigPtr_->getHorizon();
+  const int np = static_cast<int>(reference_.size1());
+  if (B <= 0) throw std::invalid_argument("batch size must be positive");
+  if (static_cast<long long>(frames.size()) != static_cast<long long>(B) * nf)
+    throw std::invalid_argument("State dimension mismatch in batch");
+  if (static_cast<long long>(references.size()) != static_cast<long long>(B) * np)
+    throw std::invalid_argument("Reference dimension mismatch in batch");
+  try {
+    if (!OSQPSolverPtr_) throw std::runtime_error("genSolver() has not been called");
+    if (batchSize_ != B) {  // first call (or new batch size): every instance starts from x = 0
+      batchTrajectory_.assign(static_cast<size_t>(B) * N, 0.0);
+      batchSize_ = B;
+    }
+    DM lbx = DM::vertcat(OCPConfigPtr_->getLowerBounds());
+    DM ubx = DM::vertcat(OCPConfigPtr_->getUpperBounds());
+    DM lbg = DM::vertcat(getConstraintLowerBounds());
+    DM ubg = DM::vertcat(getConstraintUpperBounds());
+    OSQPSolverPtr_->getOptimalSolutionBatch(B, frames, references, lbx, ubx, lbg, ubg, batchTrajectory_,
+                                            batchObjective_, &batchStats_);
+  } catch (const std::exception& e) {
+    throw std::runtime_error("Optimization failed: " + std::string(e.what()));
+  }
+  return batchTrajectory_;
+}
+
+void OptimalControlProblem::resetWarmStart() {
+  firstTime_ = true;
+  batchSize_ = 0;
+  batchTrajectory_.clear();
+  if (OSQPSolverPtr_) OSQPSolverPtr_->resetIterate();
+}
+
+void OptimalControlProblem::addScalarCost(const SX& cost) { costs_.push_back(cost); }
+
+void OptimalControlProblem::addInequalityConstraint(const std::string& constraintName, const DM& lowerBound,
+                                                    const SX& expression, const DM& upperBound) {
+  if (lowerBound.size1() != expression.size1() || expression.size1() != upperBound.size1())
+    throw std::invalid_argument("SX used for inequality constraints has different dimensions!");
+  if (lowerBound.size2() != 1 || expression.size2() != 1 || upperBound.size2() != 1)
+    throw std::invalid_argument("SX used for inequality constraints has invalid column number!");
+  constraints_.push_back(expression);
+  constraintNames_.insert(constraintNames_.end(), static_cast<size_t>(expression.size1()), constraintName);
+  constraintLowerBounds_.push_back(lowerBound);
+  constraintUpperBounds_.push_back(upperBound);
+}
+
+void OptimalControlProblem::addEquationConstraint(const std::string& constraintName, const SX& leftSX,
+                                                  const SX& rightSX) {
+  if (leftSX.size1() != rightSX.size1())
+    throw std::invalid_argument("SX used for constraints has different dimension!");
+  if (leftSX.size2() != 1 || rightSX.size2() != 1)
+    throw std::invalid_argument("SX used for constraints has invalid column number!");
+  constraints_.push_back(leftSX - rightSX);
+  constraintNames_.insert(constraintNames_.end(), static_cast<size_t>(leftSX.size1()), constraintName);
+  constraintLowerBounds_.push_back(DM::zeros(leftSX.size1()));
+  constraintUpperBounds_.push_back(DM::zeros(leftSX.size1()));
+}
+
+void OptimalControlProblem::addEquationConstraint(const std::string& constraintName, const SX& expression) {
+  if (expression.size2() != 1) throw std::invalid_argument("SX used for constraints has invalid column number!");
+  addEquationConstraint(constraintName, expression, SX::zeros(expression.size1()));
+}
+
+SX OptimalControlProblem::getCostFunction() {
+  totalCost_ = SX::zeros(1);
+  for (const SX& c : costs_) totalCost_ += c;
+  return totalCost_;
+}
+
+void OptimalControlProblem::addVectorCost(const DM& param, const SX& cost) {
+  if (param.size1() != cost.size1()) {
+    std::cout << "cost vector and weight vector have different dimensions; cost ignored\n";
+    return;  // the reference silently drops the cost here (:575-578)
+  }
+  SX weighted = SX::zeros(1, 1);
+  for (int i = 0; i < cost.size1(); ++i) weighted += param(i).scalar() * cost(i) * cost(i);
+  addScalarCost(weighted);
+}
+
+void OptimalControlProblem::addVectorCost(const std::vector<double>& param, const SX& cost) {
+  if (static_cast<casadi::casadi_int>(param.size()) != cost.size1()) {
+    std::cout << "cost vector and weight vector have different dimensions\n";
+    exit(-5);  // same exit code as the reference (:591)
+  }
+  SX weighted = SX::zeros(1, 1);
+  for (int i = 0; i < cost.size1(); ++i) weighted += param[i] * cost(i) * cost(i);
+  addScalarCost(weighted);
+}
+
+void OptimalControlProblem::setSolverType(SolverSettings::SolverType type) { solverSettings.solverType = type; }
+OptimalControlProblem::SolverSettings::SolverType OptimalControlProblem::getSolverType() const {
+  return solverSettings.solverType;
+}
+SX OptimalControlProblem::getReference() const { return reference_; }
+DM OptimalControlProblem::getOptimalTrajectory() { return optimalTrajectory_; }
+std::vector<SX> OptimalControlProblem::getConstraints() const { return constraints_; }
+casadi::DMVector OptimalControlProblem::getConstraintLowerBounds() const { return constraintLowerBounds_; }
+casadi::DMVector OptimalControlProblem::getConstraintUpperBounds() const { return constraintUpperBounds_; }
+void OptimalControlProblem::setReference(const SX& reference) { reference_ = reference; }
+
+bool OptimalControlProblem::solverInputCheck(std::map<std::string, DM> arg) const {
+  auto mismatch = [](const std::string& name, long expected, long actual) {
+    std::cerr << name << " has the wrong dimension: expected " << expected << ", got " << actual << std::endl;
+    return false;
+  };
+  const long ng = DM::vertcat(getConstraintLowerBounds()).size1();
+  if (arg["lbg"].size1() != ng) return mismatch("lbg", ng, arg["lbg"].size1());
+  if (arg["ubg"].size1() != ng) return mismatch("ubg", ng, arg["ubg"].size1());
+  const long N = OCPConfigPtr_->getVariables().size1();
+  if (arg["lbx"].size1() != N) return mismatch("lbx", N, arg["lbx"].size1());
+  if (arg["ubx"].size1() != N) return mismatch("ubx", N, arg["ubx"].size1());
+  if (arg["x0"].size1() != N) return mismatch("x0", N, arg["x0"].size1());
+  const long np = reference_.size1();
+  if (arg["p"].size1() != np) return mismatch("p", np, arg["p"].size1());
+  if (solverSettings.verbose)
+    std::cout << "dimension check passed: lbg/ubg " << ng << ", lbx/ubx/x0 " << N << ", p " << np << std::endl;
+  return true;
+}
+
+std::ostream& operator<<(std::ostream& os, const OptimalControlProblem& ocp) {
+  os << "OptimalControlProblem(horizon=" << ocp.OCPConfigPtr_->getHorizon()
+     << ", frame=" << ocp.OCPConfigPtr_->getFrameSize() << ", dt=" << ocp.OCPConfigPtr_->getDt()
+     << ", constraints=" << ocp.getConstraints().size() << ")";
+  return os;
+}
