@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- batched OCP SQP solves/sec (H=20 quadrotor MPC) on N B200s, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one batched CUDA_SQP solve of B instances per GPU (BASELINE.json configs[2]:
+quadrotor nx=12 nu=4 H=20, B=4096 random initial states, SQP_step alpha=0.1, ADMM_step
+step_num=10, OSQP settings of SQPOptimizationSolver.cpp:81-85), every step from the same cold
+iterate x=0 so that all steps do identical work.
+
+  value   solves/s, whole job, inputs resident in HBM, CUDA events around ocp_b200_solve_batch_device
+  e2e     same through ocp_b200_solve_batch with pinned HOST buffers (H2D + D2H inside the timed region)
+  roofline  admm_solve_kernel: algorithmic bytes (SURVEY.md §8d / DESIGN.md) from the per-instance
+            ADMM / PCG / check counts in the stats buffer, over its CUDA-event time
+  cpu_baseline  the oracle (restated reference CPU path) on the host cores, bounded sample
+
+`--impl reference` times the oracle alone (rank 0 only).  torch is used for device memory,
+streams, events and torch.distributed -- not for compute.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "batched OCP SQP solves/sec (H=20)"
+UNIT = "solves/s"
+SEED = 0xB200 + 2          # 0xB200 + config index
+PROBLEM = "quadrotor"
+ALPHA, STEP_NUM = 0.1, 10
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (weak scaling)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-solves", type=int, default=50)
+    return ap.parse_args()
+
+
+def workload_config(batch, n_gpus):
+    return {"workload": f"quadrotor MPC nx=12 nu=4 H=20 dt=0.005, multiple shooting RK4, {batch} random initial states per GPU "
+                        f"(BASELINE.json configs[2])",
+            "solve_method": "CUDA_SQP", "SQP_step": ALPHA, "ADMM_step": STEP_NUM, "eps_abs": 1e-3, "eps_rel": 1e-3,
+            "admm_max_iter": 10000, "batch_per_gpu": batch, "parallelism": f"instances sharded over {n_gpus} GPU(s), no data-path collective",
+            "l2": "flushed between timed steps (256 MiB write); per-step QP buffers (163 MB at B=4096) also exceed L2"}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_run(sample: int, threads: int, repeats: int = 1, warmup: int = 0):
+    import _oracle
+    ora = _oracle.OracleProblem(PROBLEM, alpha=ALPHA, step_num=STEP_NUM)
+    frames, refs = ora.sample_inputs(sample, SEED)
+    times = []
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter()
+        ora.solve_batch(frames, refs, nthreads=threads)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or max(64, 8 * threads)
+    times = cpu_run(sample, threads, repeats=args.steps, warmup=args.warmup)
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "config": workload_config(args.batch, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} of the workload's instances per step, one instance per host thread at a time; "
+                                       "oracle = FP64 restatement of the reference's CPU SQP+OSQP path (CasADi/OSQP are not "
+                                       "installable here), cold OSQP set-up every SQP step like the reference"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(dims, nnz_pu, stats, ocp):
+    """SURVEY.md §8d, summed over the instances of one batched solve (all its SQP steps)."""
+    n, m, nnz_a = dims["n"], dims["m"], dims["nnz_a"]
+    iters = stats[:, ocp.STAT["admm_iters"]].sum()
+    pcg = stats[:, ocp.STAT["pcg_iters"]].sum()
+    checks = stats[:, ocp.STAT["checks"]].sum()
+    mat = nnz_pu + 2 * nnz_a
+    admm = 8.0 * ((pcg + iters) * mat + iters * (2 * nnz_a + 8 * n + 12 * m) + pcg * (6 * n + 2 * m))
+    check = 8.0 * checks * (mat + 4 * n + 4 * m)
+    return admm + check, dict(admm_iters=float(iters), pcg_iters=float(pcg), checks=float(checks))
+
+
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import optimal_control_problem_b200 as ocp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible and there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+
+    prob = ocp.Problem(PROBLEM, alpha=ALPHA, step_num=STEP_NUM)
+    # one handle per (process, device): the problem's own handle lives on device 0 of the process's
+    # view, so create the handle explicitly on this rank's device
+    sol = ocp.Solver.create(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, prob.a_colptr, prob.a_rowidx,
+                            settings=prob.get_settings(), np_=prob.np_, nf=prob.nf, horizon=prob.horizon,
+                            model_library=prob.model_library, device=local)
+    dims = prob.dims
+    nnz_pu = int(sum(1 for j in range(prob.n) for k in range(prob.h_colptr[j], prob.h_colptr[j + 1]) if prob.h_rowidx[k] <= j))
+
+    frames_h, refs_h = prob.sample_inputs(B, SEED + 1000 * rank)
+    f64 = dict(dtype=torch.float64, device=dev)
+    d_frames = torch.from_numpy(frames_h).to(dev); d_p = torch.from_numpy(refs_h).to(dev)
+    d_lbx = torch.from_numpy(prob.lbx).to(dev); d_ubx = torch.from_numpy(prob.ubx).to(dev)
+    d_lbg = torch.from_numpy(prob.lbg).to(dev); d_ubg = torch.from_numpy(prob.ubg).to(dev)
+    d_x = torch.zeros(B, prob.N, **f64); d_f = torch.zeros(B, **f64); d_stats = torch.zeros(B, ocp.NSTATS, **f64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if world > 1:
+        g_x = torch.empty(world * B, prob.N, **f64); g_stats = torch.empty(world * B, ocp.NSTATS, **f64)
+    stream = torch.cuda.current_stream()
+
+    def device_step():
+        d_x.zero_()
+        sol.solve_batch_device(B, d_frames.data_ptr(), d_p.data_ptr(), d_lbx.data_ptr(), d_ubx.data_ptr(),
+                               d_lbg.data_ptr(), d_ubg.data_ptr(), d_x.data_ptr(), d_f.data_ptr(), d_stats.data_ptr(),
+                               stream.cuda_stream)
+        if world > 1:  # the one collective of the path: gather solutions and statistics
+            dist.all_gather_into_tensor(g_x, d_x)
+            dist.all_gather_into_tensor(g_stats, d_stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    launches0 = sol.launch_count()
+    sol.set_profiling(True)
+    sol.get_profile(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                   # L2 flush, outside the event pair
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        device_step()
+        e1.record(stream)
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    prof = sol.get_profile(reset=True)
+    sol.set_profiling(False)
+    launches = sol.launch_count() - launches0
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    stats_h = d_stats.cpu().numpy()
+    solved = int((stats_h[:, ocp.STAT["qp_status"]] == ocp.QP_SOLVED).sum())
+    bytes_per_solve_call, counts = algorithmic_bytes(dims, nnz_pu, stats_h, ocp)
+    admm_ms_per_launch = prof["admm"]["ms"] / max(1, prof["admm"]["launches"])
+    bytes_per_launch = bytes_per_solve_call / STEP_NUM
+    achieved = bytes_per_launch / (admm_ms_per_launch * 1e-3) / 1e9 if admm_ms_per_launch > 0 else 0.0
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    traffic = None
+    tpath = ROOT / "profiles" / "admm_traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+
+    # ---- e2e: pinned host buffers through ocp_b200_solve_batch -----------------------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hp_frames, hp_refs = pin(frames_h), pin(refs_h)
+    hp_x = torch.zeros(B, prob.N, dtype=torch.float64).pin_memory()
+    hp_f = torch.zeros(B, dtype=torch.float64).pin_memory()
+    hp_st = torch.zeros(B, ocp.NSTATS, dtype=torch.float64).pin_memory()
+    nx, nf_, nst = hp_x.numpy(), hp_f.numpy(), hp_st.numpy()
+
+    def host_step():
+        nx[:] = 0.0
+        sol.solve_batch(hp_frames.numpy(), hp_refs.numpy(), prob.lbx, prob.ubx, prob.lbg, prob.ubg, nx, nf_, nst)
+
+    for _ in range(2):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+    h2d = 8 * (B * (prob.nf + prob.np_ + prob.N) + 2 * prob.N + 2 * prob.ng)
+    d2h = 8 * B * (prob.N + 1 + ocp.NSTATS)
+    e2e_match = float(np.abs(nx - d_x.cpu().numpy()).max())
+
+    # ---- p50 single-solve latency (B = 1, host API) ----------------------------------------------
+    lat = []
+    if rank == 0 and args.latency_solves > 0:
+        x1 = np.zeros((1, prob.N)); f1 = np.zeros(1)
+        for i in range(args.latency_solves + 5):
+            x1[:] = 0.0
+            t0 = time.perf_counter()
+            sol.solve_batch(frames_h[i % B:i % B + 1], refs_h[i % B:i % B + 1], prob.lbx, prob.ubx, prob.lbg, prob.ubg, x1, f1)
+            if i >= 5:
+                lat.append(1e3 * (time.perf_counter() - t0))
+
+    # ---- CPU baseline on rank 0 at N = 1 ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = args.cpu_sample or max(64, 16 * threads)
+        t = cpu_run(sample, threads, repeats=1, warmup=0)[0]
+        t1 = cpu_run(min(sample, 32), 1, repeats=1, warmup=0)[0] / min(sample, 32)
+        cpu = {"value": sample / t, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{sample} instances of the same workload (first of the {B}), one instance per host thread at a time, "
+                         f"{t:.1f} s wall; single-thread {1e3 * t1:.1f} ms/solve",
+               "single_thread_ms_per_solve": 1e3 * t1}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "b200", "config": workload_config(B, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "max_abs_diff_vs_device_path": e2e_match},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "kernel": "admm_solve_kernel", "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": admm_ms_per_launch,
+                             "kernel_share_of_step": prof["admm"]["ms"] / max(total_ms, 1e-9),
+                             "assemble_ms_per_launch": prof["assemble"]["ms"] / max(1, prof["assemble"]["launches"]),
+                             "counts_per_batched_solve": counts},
+                "cpu_baseline": cpu,
+                "clocks": clocks,
+                "latency_p50_ms": float(np.median(lat)) if lat else None,
+                "solved_fraction": solved / B,
+                "device": torch.cuda.get_device_name(local), "resident": sol.device_dims()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

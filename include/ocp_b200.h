@@ -184,6 +184,15 @@ int ocp_b200_admm_trace(ocp_b200_solver* s, const double* h_vals, const double* 
 
 /* counters for bench.py: kernels launched by this handle since creation */
 long long ocp_b200_launch_count(const ocp_b200_solver* s);
+/* Optional per-kernel device timing for bench.py's roofline: when enabled, every kernel launch
+ * of this handle is bracketed by a CUDA event pair on the launching stream.  get_profile waits
+ * for the recorded events and returns accumulated milliseconds and launch counts per kind. */
+#define OCP_B200_NPROF 3
+#define OCP_B200_PROF_ADMM      0  /* admm_solve_kernel (one launch per SQP step)   */
+#define OCP_B200_PROF_ASSEMBLE  1  /* stage-library assembly kernel                 */
+#define OCP_B200_PROF_OBJECTIVE 2  /* objective + stats store                       */
+int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled);
+int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int reset);
 /* dimensions of a handle: n, m, nnz_h, nnz_a, shared memory bytes per instance, resident (1) or streaming (0) */
 int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int* nnz_a,
                       int* smem_bytes, int* resident);

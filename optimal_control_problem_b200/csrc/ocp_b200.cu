@@ -1,0 +1,626 @@
+// ocp_b200.cu -- implementation of the C ABI in include/ocp_b200.h.
+//
+// Host side of the B200 CUDA_SQP path: owns the device copies of the index structures,
+// the per-batch QP buffers and the stage library, and drives the SQP loop
+// (SQPOptimizationSolver.cpp:127-216 of the reference) as a fixed launch sequence
+//   for step in 0..step_num-1:  assemble (stage library)  ->  admm_solve_kernel (+ x update)
+//   objective (stage library) -> store_objective
+// with no host round trip between the launches.  There is no CPU path in this file: without
+// a CUDA device every entry point that computes returns OCP_B200_ERR_NO_DEVICE.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "admm_kernel.cuh"
+#include "ocp_b200_model.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? OCP_B200_ERR_NO_DEVICE \
+                                                                               : OCP_B200_ERR_CUDA, \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                         \
+  } while (0)
+
+using ocpb200::idx_t;
+using ocpb200::PatternDev;
+using ocpb200::SolveArgs;
+
+typedef const ocp_b200_model_info* (*model_info_fn)(void);
+typedef int (*model_assemble_fn)(int, const double*, const double*, const double*, const double*, const double*,
+                                 const double*, const double*, double*, int, double*, int, double*, int, double*,
+                                 double*, int, void*);
+typedef int (*model_objective_fn)(int, const double*, const double*, double*, void*);
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t count) {
+    if (count <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = count;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+int pad8(int v) { return (v + 7) & ~7; }
+
+}  // namespace
+
+struct ocp_b200_solver {
+  // problem
+  int np = 0, nf = 0, horizon = 0, ng = 0, n = 0, m = 0, N = 0, nnz_h = 0, nnz_a = 0, nnz_p = 0;
+  int device = 0;
+  std::vector<int> h_colptr, h_rowidx, a_colptr, a_rowidx;
+  ocp_b200_settings settings;
+  // device index structures
+  PatternDev pat{};
+  DevBuf<idx_t> d_idx;
+  DevBuf<int> d_int;
+  // stage library
+  void* lib = nullptr;
+  model_assemble_fn assemble = nullptr;
+  model_objective_fn objective = nullptr;
+  // launch configuration
+  int num_sms = 0, threads = 512, resident = 0, smem_bytes = 0, max_ctas = 0;
+  size_t slab_doubles = 0;
+  // workspaces (device)
+  DevBuf<double> hv, q, av, l, u, solx, soly, info, slab, trace;
+  DevBuf<double> x, p, frames, lbx, ubx, lbg, ubg, f, stats;
+  DevBuf<int> counter;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // optional per-kernel timing (ocp_b200_set_profiling): event pairs around every launch
+  int profiling = 0;
+  std::vector<cudaEvent_t> ev;      // pairs: start, stop
+  std::vector<int> ev_kind;         // OCP_B200_PROF_* of each pair
+  double prof_ms[OCP_B200_NPROF] = {0, 0, 0};
+  long long prof_count[OCP_B200_NPROF] = {0, 0, 0};
+};
+
+namespace {
+
+int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
+  const int n = s->n, m = s->m;
+  const std::vector<int>&ac = s->a_colptr, &ar = s->a_rowidx, &hc = s->h_colptr, &hr = s->h_rowidx;
+  // CSR view of A with the permutation back to CSC positions
+  std::vector<int> rowptr(m + 1, 0), colidx(s->nnz_a), perm(s->nnz_a);
+  for (int k = 0; k < s->nnz_a; ++k) rowptr[ar[k] + 1]++;
+  for (int i = 0; i < m; ++i) rowptr[i + 1] += rowptr[i];
+  {
+    std::vector<int> next(rowptr.begin(), rowptr.end() - 1);
+    for (int j = 0; j < n; ++j)
+      for (int k = ac[j]; k < ac[j + 1]; ++k) { const int t = next[ar[k]]++; colidx[t] = j; perm[t] = k; }
+  }
+  // P: full symmetric pattern mirrored from the UPPER triangle of H (OsqpEigen hands OSQP the
+  // upper triangle only); p_src = position of the upper-triangle twin in the caller's values
+  std::vector<std::vector<std::pair<int, int>>> cols(n);
+  for (int j = 0; j < n; ++j)
+    for (int k = hc[j]; k < hc[j + 1]; ++k) {
+      const int i = hr[k];
+      if (i > j) continue;
+      cols[j].push_back({i, k});
+      if (i != j) cols[i].push_back({j, k});
+    }
+  std::vector<int> pc(n + 1, 0), pr, psrc;
+  for (int j = 0; j < n; ++j) {
+    std::sort(cols[j].begin(), cols[j].end());
+    for (auto& e : cols[j]) { pr.push_back(e.first); psrc.push_back(e.second); }
+    pc[j + 1] = static_cast<int>(pr.size());
+  }
+  s->nnz_p = static_cast<int>(pr.size());
+  // preconditioner blocks
+  std::vector<int> blk;
+  if (num_blocks > 0 && block_ptr) {
+    blk.assign(block_ptr, block_ptr + num_blocks + 1);
+    if (blk.front() != 0 || blk.back() != n) return fail(OCP_B200_ERR_INVALID, "block_ptr must run from 0 to n");
+    for (int b = 0; b < num_blocks; ++b)
+      if (blk[b + 1] <= blk[b]) return fail(OCP_B200_ERR_INVALID, "block_ptr must be strictly ascending");
+  } else {
+    // default: [p | frame 0 | ... | frame H-1]; blocks wider than 64 columns (a QP-only handle
+    // is one "frame") are cut into 32-column pieces
+    std::vector<int> cuts{0};
+    if (s->np > 0) cuts.push_back(s->np);
+    for (int k = 0; k < s->horizon; ++k) cuts.push_back(s->np + (k + 1) * s->nf);
+    blk.push_back(0);
+    for (size_t b = 0; b + 1 < cuts.size(); ++b) {
+      if (cuts[b + 1] - cuts[b] > 64)
+        for (int j = cuts[b] + 32; j < cuts[b + 1]; j += 32) blk.push_back(j);
+      blk.push_back(cuts[b + 1]);
+    }
+  }
+  const int nblk = static_cast<int>(blk.size()) - 1;
+  std::vector<int> blk_of(n), minv_off(nblk);
+  int minv = 0, max_bs = 0;
+  for (int b = 0; b < nblk; ++b) {
+    const int bs = blk[b + 1] - blk[b];
+    minv_off[b] = minv;
+    minv += bs * bs;
+    max_bs = std::max(max_bs, bs);
+    for (int j = blk[b]; j < blk[b + 1]; ++j) blk_of[j] = b;
+  }
+  // Gauss-Jordan on large dense blocks is pointless (and the block store would not fit):
+  // fall back to Jacobi for such partitions
+  if (max_bs > 64) return fail(OCP_B200_ERR_UNSUPPORTED, "preconditioner blocks larger than 64 columns are not supported");
+  std::vector<int> rows_long, rows_short;
+  for (int i = 0; i < m; ++i) (rowptr[i + 1] - rowptr[i] >= 8 ? rows_long : rows_short).push_back(i);
+
+  if (n + 1 > 65535 || m + 1 > 65535 || s->nnz_a > 65535 || s->nnz_p > 65535)
+    return fail(OCP_B200_ERR_UNSUPPORTED, "problem too large for 16-bit index structures (n, m, nnz < 65536)");
+
+  // one idx_t arena, every array padded to 8 entries so that the shared-memory copy keeps alignment
+  std::vector<idx_t> arena;
+  auto push = [&](const std::vector<int>& v) {
+    const size_t off = arena.size();
+    for (int x : v) arena.push_back(static_cast<idx_t>(x));
+    while (arena.size() % 8) arena.push_back(0);
+    return off;
+  };
+  const size_t o_acp = push(ac), o_ari = push(ar), o_arp = push(rowptr), o_aci = push(colidx), o_perm = push(perm),
+               o_pcp = push(pc), o_pri = push(pr), o_blk = push(blk), o_bof = push(blk_of), o_rl = push(rows_long),
+               o_rs = push(rows_short);
+  CUDA_TRY(s->d_idx.reserve(arena.size()));
+  CUDA_TRY(cudaMemcpy(s->d_idx.p, arena.data(), arena.size() * sizeof(idx_t), cudaMemcpyHostToDevice));
+  std::vector<int> iarena(psrc);
+  const size_t o_minv = iarena.size();
+  iarena.insert(iarena.end(), minv_off.begin(), minv_off.end());
+  CUDA_TRY(s->d_int.reserve(iarena.size()));
+  CUDA_TRY(cudaMemcpy(s->d_int.p, iarena.data(), iarena.size() * sizeof(int), cudaMemcpyHostToDevice));
+
+  PatternDev& P = s->pat;
+  P.n = n; P.m = m; P.nnz_a = s->nnz_a; P.nnz_p = s->nnz_p; P.nnz_h = s->nnz_h;
+  P.nblk = nblk; P.minv_doubles = std::max(minv, n); P.max_bs = max_bs;
+  P.n_long = static_cast<int>(rows_long.size()); P.n_short = static_cast<int>(rows_short.size());
+  const idx_t* base = s->d_idx.p;
+  P.a_colptr = base + o_acp; P.a_rowidx = base + o_ari; P.a_rowptr = base + o_arp; P.a_colidx = base + o_aci;
+  P.a_perm = base + o_perm; P.p_colptr = base + o_pcp; P.p_rowidx = base + o_pri; P.blk_ptr = base + o_blk;
+  P.blk_of_col = base + o_bof; P.rows_long = base + o_rl; P.rows_short = base + o_rs;
+  P.p_src = s->d_int.p; P.minv_off = s->d_int.p + o_minv;
+
+  // shared-memory budget of the resident variant: state + staged index arrays
+  const size_t idx_entries = size_t(pad8(n + 1)) * 2 + size_t(pad8(s->nnz_a)) * 3 + pad8(m + 1) + pad8(s->nnz_p) +
+                             pad8(nblk + 1) + pad8(n) + pad8(P.n_long) + pad8(P.n_short);
+  const size_t want = ocpb200::work_doubles(P) * sizeof(double) + idx_entries * sizeof(idx_t);
+  int max_optin = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+  cudaFuncAttributes fa{};
+  CUDA_TRY(cudaFuncGetAttributes(&fa, ocpb200::admm_solve_kernel<true>));
+  const size_t avail = size_t(max_optin) - fa.sharedSizeBytes;
+  s->resident = want <= avail ? 1 : 0;
+  s->smem_bytes = s->resident ? static_cast<int>(want) : 0;
+  if (s->resident)
+    CUDA_TRY(cudaFuncSetAttribute(ocpb200::admm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  s->smem_bytes));
+  s->slab_doubles = (ocpb200::work_doubles(P) + 15) & ~size_t(15);
+  int per_sm = 1;
+  if (s->resident)
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ocpb200::admm_solve_kernel<true>, s->threads,
+                                                           s->smem_bytes));
+  else
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ocpb200::admm_solve_kernel<false>, s->threads, 0));
+  s->max_ctas = std::max(1, per_sm) * s->num_sms;
+  return OCP_B200_OK;
+}
+
+int load_model(ocp_b200_solver* s, const char* path) {
+  s->lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!s->lib) return fail(OCP_B200_ERR_MODEL, std::string("cannot load stage library: ") + dlerror());
+  model_info_fn info_fn = reinterpret_cast<model_info_fn>(dlsym(s->lib, "ocp_b200_model_get_info"));
+  s->assemble = reinterpret_cast<model_assemble_fn>(dlsym(s->lib, "ocp_b200_model_assemble"));
+  s->objective = reinterpret_cast<model_objective_fn>(dlsym(s->lib, "ocp_b200_model_objective"));
+  if (!info_fn || !s->assemble || !s->objective)
+    return fail(OCP_B200_ERR_MODEL, "stage library does not export the ocp_b200_model.h symbols");
+  const ocp_b200_model_info* mi = info_fn();
+  if (!mi || mi->abi_version != OCP_B200_MODEL_ABI_VERSION)
+    return fail(OCP_B200_ERR_MODEL, "stage library ABI version mismatch");
+  if (mi->np != s->np || mi->nf != s->nf || mi->horizon != s->horizon || mi->ng != s->ng || mi->nnz_h != s->nnz_h ||
+      mi->nnz_a != s->nnz_a)
+    return fail(OCP_B200_ERR_MODEL, "stage library was generated for a different problem shape");
+  if (std::memcmp(mi->h_colptr, s->h_colptr.data(), sizeof(int) * (s->n + 1)) ||
+      std::memcmp(mi->h_rowidx, s->h_rowidx.data(), sizeof(int) * s->nnz_h) ||
+      std::memcmp(mi->a_colptr, s->a_colptr.data(), sizeof(int) * (s->n + 1)) ||
+      std::memcmp(mi->a_rowidx, s->a_rowidx.data(), sizeof(int) * s->nnz_a))
+    return fail(OCP_B200_ERR_MODEL, "stage library sparsity pattern differs from the problem description");
+  return OCP_B200_OK;
+}
+
+int check_settings(const ocp_b200_settings* t) {
+  if (!t) return fail(OCP_B200_ERR_INVALID, "settings is NULL");
+  if (t->sqp_step_num < 0 || t->admm_max_iter < 1 || t->check_termination < 0 || t->scaling_iters < 0 ||
+      t->pcg_max_iter < 1 || !(t->rho > 0) || !(t->sigma > 0) || !(t->relax > 0 && t->relax < 2) ||
+      !(t->eps_abs >= 0) || !(t->eps_rel >= 0) || !(t->pcg_tol > 0) || t->pcg_precond < 0 ||
+      t->pcg_precond > OCP_B200_PRECOND_BLOCK_JACOBI)
+    return fail(OCP_B200_ERR_INVALID, "settings out of range");
+  return OCP_B200_OK;
+}
+
+// event pair around one launch when profiling is on
+struct ProfScope {
+  ocp_b200_solver* s; cudaStream_t st; cudaEvent_t stop = nullptr;
+  ProfScope(ocp_b200_solver* s_, int kind, cudaStream_t st_) : s(s_), st(st_) {
+    if (!s->profiling) return;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    s->ev.push_back(a); s->ev.push_back(b); s->ev_kind.push_back(kind);
+    cudaEventRecord(a, st);
+    stop = b;
+  }
+  ~ProfScope() { if (stop) cudaEventRecord(stop, st); }
+};
+
+// one ADMM launch over B instances
+int launch_admm(ocp_b200_solver* s, SolveArgs& A, cudaStream_t st) {
+  CUDA_TRY(s->counter.reserve(1));
+  CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
+  A.counter = s->counter.p;
+  const int grid = std::min(A.B, s->max_ctas);
+  ProfScope prof(s, OCP_B200_PROF_ADMM, st);
+  if (s->resident) {
+    A.slab = nullptr; A.slab_doubles = 0;
+    ocpb200::admm_solve_kernel<true><<<grid, s->threads, s->smem_bytes, st>>>(s->pat, s->settings, A);
+  } else {
+    CUDA_TRY(s->slab.reserve(size_t(grid) * s->slab_doubles));
+    A.slab = s->slab.p; A.slab_doubles = s->slab_doubles;
+    ocpb200::admm_solve_kernel<false><<<grid, s->threads, 0, st>>>(s->pat, s->settings, A);
+  }
+  CUDA_TRY(cudaGetLastError());
+  s->launches++;
+  return OCP_B200_OK;
+}
+
+int reserve_qp(ocp_b200_solver* s, int B) {
+  CUDA_TRY(s->hv.reserve(size_t(B) * s->nnz_h));
+  CUDA_TRY(s->q.reserve(size_t(B) * s->n));
+  CUDA_TRY(s->av.reserve(size_t(B) * s->nnz_a));
+  CUDA_TRY(s->l.reserve(size_t(B) * s->m));
+  CUDA_TRY(s->u.reserve(size_t(B) * s->m));
+  return OCP_B200_OK;
+}
+
+int assemble_on(ocp_b200_solver* s, int B, const double* x, const double* p, const double* frames,
+                const double* lbx, const double* ubx, const double* lbg, const double* ubg, cudaStream_t st) {
+  if (!s->assemble) return fail(OCP_B200_ERR_MODEL, "this handle has no stage library (QP-only handle)");
+  ProfScope prof(s, OCP_B200_PROF_ASSEMBLE, st);
+  const int rc = s->assemble(B, x, p, frames, lbx, ubx, lbg, ubg, s->hv.p, s->nnz_h, s->q.p, s->n, s->av.p,
+                             s->nnz_a, s->l.p, s->u.p, s->m, st);
+  if (rc != 0) return fail(OCP_B200_ERR_CUDA, std::string("stage assembly launch: ") +
+                                                  cudaGetErrorString(static_cast<cudaError_t>(rc)));
+  s->launches++;
+  return OCP_B200_OK;
+}
+
+int h2d(double* dst, const double* src, size_t count, cudaStream_t st) {
+  if (count == 0) return OCP_B200_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, st));
+  return OCP_B200_OK;
+}
+int d2h(double* dst, const double* src, size_t count, cudaStream_t st) {
+  if (count == 0) return OCP_B200_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return OCP_B200_OK;
+}
+
+#define RC_TRY(expr) do { int rc_ = (expr); if (rc_ != OCP_B200_OK) return rc_; } while (0)
+
+int upload_problem_inputs(ocp_b200_solver* s, int B, const double* frames, const double* p, const double* lbx,
+                          const double* ubx, const double* lbg, const double* ubg, cudaStream_t st) {
+  CUDA_TRY(s->p.reserve(size_t(B) * s->np));
+  CUDA_TRY(s->frames.reserve(size_t(B) * s->nf));
+  CUDA_TRY(s->lbx.reserve(s->N)); CUDA_TRY(s->ubx.reserve(s->N));
+  CUDA_TRY(s->lbg.reserve(s->ng)); CUDA_TRY(s->ubg.reserve(s->ng));
+  RC_TRY(h2d(s->p.p, p, size_t(B) * s->np, st));
+  if (frames) RC_TRY(h2d(s->frames.p, frames, size_t(B) * s->nf, st));
+  RC_TRY(h2d(s->lbx.p, lbx, s->N, st)); RC_TRY(h2d(s->ubx.p, ubx, s->N, st));
+  RC_TRY(h2d(s->lbg.p, lbg, s->ng, st)); RC_TRY(h2d(s->ubg.p, ubg, s->ng, st));
+  return OCP_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ocp_b200_default_settings(ocp_b200_settings* s) {
+  if (!s) return;
+  s->sqp_alpha = 0.1; s->sqp_step_num = 10;          // OptimalControlProblem.h:24-27
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3;              // SQPOptimizationSolver.cpp:83-84
+  s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->admm_max_iter = 10000;                          // SQPOptimizationSolver.cpp:85
+  s->rho = 0.1; s->sigma = 1e-6; s->relax = 1.6;
+  s->scaling_iters = 10; s->check_termination = 25;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 0; s->adaptive_rho_tolerance = 5.0;
+  s->pcg_max_iter = 500; s->pcg_tol = 1e-10; s->pcg_precond = OCP_B200_PRECOND_BLOCK_JACOBI;
+}
+
+int ocp_b200_abi_version(void) { return OCP_B200_ABI_VERSION; }
+const char* ocp_b200_last_error(void) { return g_error.c_str(); }
+
+int ocp_b200_create(const ocp_b200_problem_desc* d, const ocp_b200_settings* settings, ocp_b200_solver** out) {
+  if (!d || !out) return fail(OCP_B200_ERR_INVALID, "desc/out is NULL");
+  *out = nullptr;
+  ocp_b200_settings dflt;
+  if (!settings) { ocp_b200_default_settings(&dflt); settings = &dflt; }
+  RC_TRY(check_settings(settings));
+  if (d->np < 0 || d->nf <= 0 || d->horizon <= 0 || d->ng < 0 || !d->h_colptr || !d->a_colptr ||
+      (d->nnz_h > 0 && !d->h_rowidx) || (d->nnz_a > 0 && !d->a_rowidx))
+    return fail(OCP_B200_ERR_INVALID, "bad problem description");
+  const long long n = (long long)d->np + (long long)d->nf * d->horizon, m = n + d->ng;
+  if (n <= 0 || m > 65534) return fail(OCP_B200_ERR_UNSUPPORTED, "problem too large for 16-bit index structures");
+  if (d->h_colptr[0] != 0 || d->h_colptr[n] != d->nnz_h || d->a_colptr[0] != 0 || d->a_colptr[n] != d->nnz_a)
+    return fail(OCP_B200_ERR_INVALID, "column pointers do not match nnz");
+  for (int j = 0; j < n; ++j) {
+    if (d->h_colptr[j + 1] < d->h_colptr[j] || d->a_colptr[j + 1] < d->a_colptr[j])
+      return fail(OCP_B200_ERR_INVALID, "column pointers must be non-decreasing");
+    for (int k = d->h_colptr[j]; k < d->h_colptr[j + 1]; ++k)
+      if (d->h_rowidx[k] < 0 || d->h_rowidx[k] >= n || (k > d->h_colptr[j] && d->h_rowidx[k] <= d->h_rowidx[k - 1]))
+        return fail(OCP_B200_ERR_INVALID, "Hessian row indices must be strictly increasing within a column");
+    for (int k = d->a_colptr[j]; k < d->a_colptr[j + 1]; ++k)
+      if (d->a_rowidx[k] < 0 || d->a_rowidx[k] >= m || (k > d->a_colptr[j] && d->a_rowidx[k] <= d->a_rowidx[k - 1]))
+        return fail(OCP_B200_ERR_INVALID, "Jacobian row indices must be strictly increasing within a column");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(OCP_B200_ERR_NO_DEVICE, std::string("no CUDA device (there is no CPU fallback): ") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (d->device < 0 || d->device >= ndev) return fail(OCP_B200_ERR_INVALID, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(d->device));
+
+  ocp_b200_solver* s = new (std::nothrow) ocp_b200_solver();
+  if (!s) return fail(OCP_B200_ERR_INVALID, "out of host memory");
+  s->np = d->np; s->nf = d->nf; s->horizon = d->horizon; s->ng = d->ng;
+  s->n = static_cast<int>(n); s->m = static_cast<int>(m); s->N = d->nf * d->horizon;
+  s->nnz_h = d->nnz_h; s->nnz_a = d->nnz_a; s->device = d->device;
+  s->h_colptr.assign(d->h_colptr, d->h_colptr + n + 1); s->h_rowidx.assign(d->h_rowidx, d->h_rowidx + d->nnz_h);
+  s->a_colptr.assign(d->a_colptr, d->a_colptr + n + 1); s->a_rowidx.assign(d->a_rowidx, d->a_rowidx + d->nnz_a);
+  s->settings = *settings;
+  auto bail = [&](int rc) { std::string keep = g_error; ocp_b200_destroy(s); g_error = keep; return rc; };
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) return bail(fail(OCP_B200_ERR_CUDA, "cudaGetDeviceProperties failed"));
+  if (prop.major < 10)
+    return bail(fail(OCP_B200_ERR_UNSUPPORTED, std::string("device ") + prop.name + " is not sm_100a; this library is built for B200 only"));
+  s->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(OCP_B200_ERR_CUDA, "cudaStreamCreate failed"));
+  int rc = upload_pattern(s, d->num_blocks, d->block_ptr);
+  if (rc != OCP_B200_OK) return bail(rc);
+  if (d->model_library && d->model_library[0]) {
+    rc = load_model(s, d->model_library);
+    if (rc != OCP_B200_OK) return bail(rc);
+  }
+  *out = s;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_destroy(ocp_b200_solver* s) {
+  if (!s) return OCP_B200_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  s->d_idx.release(); s->d_int.release();
+  DevBuf<double>* bufs[] = {&s->hv, &s->q, &s->av, &s->l, &s->u, &s->solx, &s->soly, &s->info, &s->slab, &s->trace,
+                            &s->x, &s->p, &s->frames, &s->lbx, &s->ubx, &s->lbg, &s->ubg, &s->f, &s->stats};
+  for (DevBuf<double>* b : bufs) b->release();
+  s->counter.release();
+  // the stage library stays loaded: its kernels are registered with the CUDA runtime and
+  // unloading a module that another handle still uses would invalidate them
+  delete s;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_update_settings(ocp_b200_solver* s, const ocp_b200_settings* settings) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  RC_TRY(check_settings(settings));
+  s->settings = *settings;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_get_settings(const ocp_b200_solver* s, ocp_b200_settings* out) {
+  if (!s || !out) return fail(OCP_B200_ERR_INVALID, "solver/out is NULL");
+  *out = s->settings;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_solve_batch_device(ocp_b200_solver* s, int B, const double* d_frames, const double* d_p,
+                                const double* d_lbx, const double* d_ubx, const double* d_lbg,
+                                const double* d_ubg, double* d_x, double* d_f, double* d_stats, void* stream) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  if (B < 0 || (B > 0 && (!d_x || (s->np > 0 && !d_p) || !d_lbx || !d_ubx || (s->ng > 0 && (!d_lbg || !d_ubg)))))
+    return fail(OCP_B200_ERR_INVALID, "bad arguments to solve_batch");
+  if (B == 0) return OCP_B200_OK;
+  if (!s->assemble) return fail(OCP_B200_ERR_MODEL, "this handle has no stage library (QP-only handle)");
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RC_TRY(reserve_qp(s, B));
+  CUDA_TRY(s->stats.reserve(size_t(B) * OCP_B200_NSTATS));
+  CUDA_TRY(s->f.reserve(B));
+  double* stats = d_stats ? d_stats : s->stats.p;
+  double* f = d_f ? d_f : s->f.p;
+  if (s->settings.sqp_step_num == 0)
+    CUDA_TRY(cudaMemsetAsync(stats, 0, size_t(B) * OCP_B200_NSTATS * sizeof(double), st));
+  for (int step = 0; step < s->settings.sqp_step_num; ++step) {
+    RC_TRY(assemble_on(s, B, d_x, d_p, d_frames, d_lbx, d_ubx, d_lbg, d_ubg, st));
+    SolveArgs A{};
+    A.B = B;
+    A.h_vals = s->hv.p; A.ld_h = s->nnz_h; A.q = s->q.p; A.ld_n = s->n; A.a_vals = s->av.p; A.ld_a = s->nnz_a;
+    A.l = s->l.p; A.u = s->u.p; A.ld_m = s->m;
+    A.x_iter = d_x; A.np = s->np; A.N = s->N; A.sqp_alpha = s->settings.sqp_alpha;
+    A.stats = stats; A.first_step = step == 0;
+    RC_TRY(launch_admm(s, A, st));
+  }
+  {
+    ProfScope prof(s, OCP_B200_PROF_OBJECTIVE, st);
+    const int rc = s->objective(B, d_x, d_p, f, st);
+    if (rc != 0) return fail(OCP_B200_ERR_CUDA, std::string("objective launch: ") + cudaGetErrorString(static_cast<cudaError_t>(rc)));
+    s->launches++;
+    ocpb200::store_objective_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, f, stats);
+    CUDA_TRY(cudaGetLastError());
+    s->launches++;
+  }
+  return OCP_B200_OK;
+}
+
+int ocp_b200_solve_batch(ocp_b200_solver* s, int B, const double* frames, const double* p, const double* lbx,
+                         const double* ubx, const double* lbg, const double* ubg, double* x_inout, double* f_out,
+                         double* stats) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  if (B < 0 || (B > 0 && (!x_inout || (s->np > 0 && !p) || !lbx || !ubx || (s->ng > 0 && (!lbg || !ubg)))))
+    return fail(OCP_B200_ERR_INVALID, "bad arguments to solve_batch");
+  if (B == 0) return OCP_B200_OK;
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  RC_TRY(upload_problem_inputs(s, B, frames, p, lbx, ubx, lbg, ubg, st));
+  CUDA_TRY(s->x.reserve(size_t(B) * s->N));
+  CUDA_TRY(s->f.reserve(B));
+  CUDA_TRY(s->stats.reserve(size_t(B) * OCP_B200_NSTATS));
+  RC_TRY(h2d(s->x.p, x_inout, size_t(B) * s->N, st));
+  RC_TRY(ocp_b200_solve_batch_device(s, B, frames ? s->frames.p : nullptr, s->p.p, s->lbx.p, s->ubx.p, s->lbg.p,
+                                     s->ubg.p, s->x.p, s->f.p, s->stats.p, st));
+  RC_TRY(d2h(x_inout, s->x.p, size_t(B) * s->N, st));
+  if (f_out) RC_TRY(d2h(f_out, s->f.p, B, st));
+  if (stats) RC_TRY(d2h(stats, s->stats.p, size_t(B) * OCP_B200_NSTATS, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return OCP_B200_OK;
+}
+
+int ocp_b200_export_qp(ocp_b200_solver* s, int B, const double* frames, const double* p, const double* lbx,
+                       const double* ubx, const double* lbg, const double* ubg, const double* x, double* h_vals,
+                       double* q, double* a_vals, double* l, double* u) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  if (B <= 0 || !x || (s->np > 0 && !p) || !lbx || !ubx || (s->ng > 0 && (!lbg || !ubg)))
+    return fail(OCP_B200_ERR_INVALID, "bad arguments to export_qp");
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  RC_TRY(upload_problem_inputs(s, B, frames, p, lbx, ubx, lbg, ubg, st));
+  CUDA_TRY(s->x.reserve(size_t(B) * s->N));
+  RC_TRY(h2d(s->x.p, x, size_t(B) * s->N, st));
+  RC_TRY(reserve_qp(s, B));
+  RC_TRY(assemble_on(s, B, s->x.p, s->p.p, frames ? s->frames.p : nullptr, s->lbx.p, s->ubx.p, s->lbg.p, s->ubg.p, st));
+  if (h_vals) RC_TRY(d2h(h_vals, s->hv.p, size_t(B) * s->nnz_h, st));
+  if (q) RC_TRY(d2h(q, s->q.p, size_t(B) * s->n, st));
+  if (a_vals) RC_TRY(d2h(a_vals, s->av.p, size_t(B) * s->nnz_a, st));
+  if (l) RC_TRY(d2h(l, s->l.p, size_t(B) * s->m, st));
+  if (u) RC_TRY(d2h(u, s->u.p, size_t(B) * s->m, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return OCP_B200_OK;
+}
+
+static int qp_solve_common(ocp_b200_solver* s, int B, const double* h_vals, const double* q, const double* a_vals,
+                           const double* l, const double* u, double* x_out, double* y_out, double* info,
+                           int max_records, double* trace, int* n_records) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  if (B <= 0 || (s->nnz_h > 0 && !h_vals) || !q || !a_vals || !l || !u)
+    return fail(OCP_B200_ERR_INVALID, "bad arguments to qp_solve");
+  CUDA_TRY(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  RC_TRY(reserve_qp(s, B));
+  CUDA_TRY(s->solx.reserve(size_t(B) * s->n));
+  CUDA_TRY(s->soly.reserve(size_t(B) * s->m));
+  CUDA_TRY(s->info.reserve(size_t(B) * OCP_B200_NINFO));
+  RC_TRY(h2d(s->hv.p, h_vals, size_t(B) * s->nnz_h, st));
+  RC_TRY(h2d(s->q.p, q, size_t(B) * s->n, st));
+  RC_TRY(h2d(s->av.p, a_vals, size_t(B) * s->nnz_a, st));
+  RC_TRY(h2d(s->l.p, l, size_t(B) * s->m, st));
+  RC_TRY(h2d(s->u.p, u, size_t(B) * s->m, st));
+  SolveArgs A{};
+  A.B = B;
+  A.h_vals = s->hv.p; A.ld_h = s->nnz_h; A.q = s->q.p; A.ld_n = s->n; A.a_vals = s->av.p; A.ld_a = s->nnz_a;
+  A.l = s->l.p; A.u = s->u.p; A.ld_m = s->m;
+  A.sol_x = s->solx.p; A.sol_y = s->soly.p; A.info = s->info.p;
+  DevBuf<int> ntr;
+  if (trace && max_records > 0) {
+    CUDA_TRY(s->trace.reserve(size_t(max_records) * OCP_B200_TRACE_WIDTH));
+    CUDA_TRY(ntr.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(ntr.p, 0, sizeof(int), st));
+    A.trace = s->trace.p; A.max_trace = max_records; A.n_trace = ntr.p;
+  }
+  int rc = launch_admm(s, A, st);
+  if (rc == OCP_B200_OK && x_out) rc = d2h(x_out, s->solx.p, size_t(B) * s->n, st);
+  if (rc == OCP_B200_OK && y_out) rc = d2h(y_out, s->soly.p, size_t(B) * s->m, st);
+  if (rc == OCP_B200_OK && info) rc = d2h(info, s->info.p, size_t(B) * OCP_B200_NINFO, st);
+  int nrec = 0;
+  if (rc == OCP_B200_OK && A.trace) {
+    cudaError_t e = cudaMemcpyAsync(&nrec, ntr.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(OCP_B200_ERR_CUDA, cudaGetErrorString(e));
+    else rc = d2h(trace, s->trace.p, size_t(std::min(nrec, max_records)) * OCP_B200_TRACE_WIDTH, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  ntr.release();
+  if (rc != OCP_B200_OK) return rc;
+  if (e != cudaSuccess) return fail(OCP_B200_ERR_CUDA, std::string("qp_solve: ") + cudaGetErrorString(e));
+  if (n_records) *n_records = std::min(nrec, max_records);
+  return OCP_B200_OK;
+}
+
+int ocp_b200_qp_solve_batch(ocp_b200_solver* s, int B, const double* h_vals, const double* q, const double* a_vals,
+                            const double* l, const double* u, double* x_out, double* y_out, double* info) {
+  return qp_solve_common(s, B, h_vals, q, a_vals, l, u, x_out, y_out, info, 0, nullptr, nullptr);
+}
+
+int ocp_b200_admm_trace(ocp_b200_solver* s, const double* h_vals, const double* q, const double* a_vals,
+                        const double* l, const double* u, int max_records, double* trace, int* n_records,
+                        double* x_out, double* y_out) {
+  if (!trace || max_records <= 0 || !n_records) return fail(OCP_B200_ERR_INVALID, "trace buffer missing");
+  return qp_solve_common(s, 1, h_vals, q, a_vals, l, u, x_out, y_out, nullptr, max_records, trace, n_records);
+}
+
+long long ocp_b200_launch_count(const ocp_b200_solver* s) { return s ? s->launches : 0; }
+
+int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  s->profiling = enabled ? 1 : 0;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int reset) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  CUDA_TRY(cudaSetDevice(s->device));
+  for (size_t k = 0; k < s->ev_kind.size(); ++k) {
+    cudaEvent_t a = s->ev[2 * k], b = s->ev[2 * k + 1];
+    CUDA_TRY(cudaEventSynchronize(b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, a, b));
+    s->prof_ms[s->ev_kind[k]] += t;
+    s->prof_count[s->ev_kind[k]]++;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+  s->ev.clear(); s->ev_kind.clear();
+  for (int k = 0; k < OCP_B200_NPROF; ++k) {
+    if (ms) ms[k] = s->prof_ms[k];
+    if (count) count[k] = s->prof_count[k];
+    if (reset) { s->prof_ms[k] = 0; s->prof_count[k] = 0; }
+  }
+  return OCP_B200_OK;
+}
+
+int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int* nnz_a, int* smem_bytes,
+                      int* resident) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  if (n) *n = s->n;
+  if (m) *m = s->m;
+  if (nnz_h) *nnz_h = s->nnz_h;
+  if (nnz_a) *nnz_a = s->nnz_a;
+  if (smem_bytes) *smem_bytes = s->smem_bytes;
+  if (resident) *resident = s->resident;
+  return OCP_B200_OK;
+}
+
+}  // extern "C"

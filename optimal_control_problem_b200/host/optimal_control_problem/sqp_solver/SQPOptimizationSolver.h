@@ -49,6 +49,9 @@ class SQPOptimizationSolver {
   int numConstraints() const { return m_; }
   int numParameters() const { return np_; }
   void resetIterate();
+  // SQP schedule of the next solve: number of steps and step length (reference: fixed at construction)
+  void setSchedule(int stepNum, double alpha) { stepNum_ = stepNum; alpha_ = alpha; }
+  double lastObjective() const { return densify(result_.at("f")).nonzeros().at(0); }
 
  private:
   std::shared_ptr<AutoDifferentiator> objectiveFunctionAutoDifferentiatorPtr_;

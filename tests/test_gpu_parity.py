@@ -1,0 +1,219 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/ocp_b200.h), against
+the CPU oracle on the same seeded inputs.
+
+Tolerances (FP64 on both sides; the GPU solves the reduced KKT system with PCG to a relative
+residual of 1e-10 where the oracle uses an exact LDL' solve, so ADMM iterates agree to rounding
+amplified by the conditioning of the scaled KKT system):
+  * sparsity patterns / CSC index arrays: bit-exact;
+  * local-system values (H, grad, J, l - c, u - c): 1e-12 relative;
+  * QP primal / dual solutions, SQP iterates: 1e-6 relative to the vector's inf-norm
+    (BASELINE.json north_star), with identical ADMM iteration counts, rho updates and statuses.
+"""
+import numpy as np
+import pytest
+
+import _oracle
+
+pytestmark = pytest.mark.gpu
+
+REL_VALUES = 1e-12
+REL_SOLUTION = 1e-6
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def random_iterate(prob, B, seed):
+    rng = np.random.default_rng(seed)
+    frames, refs = prob.sample_inputs(B, seed)
+    x = np.tile(frames, (1, prob.horizon)) + 0.05 * rng.standard_normal((B, prob.N))
+    return frames, refs, x
+
+
+@pytest.mark.parametrize("name", ["quadrotor", "cartpole", "centroidal"])
+def test_patterns_bit_exact(problems, name):
+    prob, ora = problems(name)
+    assert prob.dims == dict(np=ora.np_, nf=ora.nf, horizon=ora.horizon, ng=ora.ng, n=ora.n, m=ora.m,
+                             nnz_h=ora.nnz_h, nnz_a=ora.nnz_a)
+    for a in ("h_colptr", "h_rowidx", "a_colptr", "a_rowidx"):
+        assert np.array_equal(getattr(prob, a), getattr(ora, a)), a
+
+
+@pytest.mark.parametrize("name,B", [("quadrotor", 5), ("cartpole", 3), ("centroidal", 3)])
+def test_local_system_matches_oracle(problems, name, B):
+    prob, ora = problems(name)
+    frames, refs, x = random_iterate(prob, B, 0xB200 + 7)
+    hv, q, av, l, u = prob.solver.export_qp(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x)
+    for b in range(B):
+        ohv, oq, oav, ol, ou = ora.local_system(frames[b], refs[b], x[b])
+        assert rel_err(hv[b], ohv) < REL_VALUES
+        assert rel_err(q[b], oq) < REL_VALUES
+        assert rel_err(av[b], oav) < REL_VALUES
+        fin = np.isfinite(ol)
+        assert np.array_equal(np.isfinite(l[b]), fin) and np.array_equal(l[b][~fin], ol[~fin])
+        assert rel_err(l[b][fin], ol[fin]) < REL_VALUES
+        fin = np.isfinite(ou)
+        assert np.array_equal(np.isfinite(u[b]), fin) and np.array_equal(u[b][~fin], ou[~fin])
+        assert rel_err(u[b][fin], ou[fin]) < REL_VALUES
+
+
+def test_local_system_without_frame_pin(problems):
+    prob, ora = problems("quadrotor")
+    frames, refs, x = random_iterate(prob, 2, 11)
+    hv, q, av, l, u = prob.solver.export_qp(None, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x)
+    for b in range(2):
+        ohv, oq, oav, ol, ou = ora.local_system(None, refs[b], x[b])
+        assert np.array_equal(np.isfinite(l[b]), np.isfinite(ol))
+        fin = np.isfinite(ol)
+        assert rel_err(l[b][fin], ol[fin]) < REL_VALUES
+        assert rel_err(av[b], oav) < REL_VALUES
+
+
+def _qp_case(prob, ora, seed, B=3):
+    frames, refs, x = random_iterate(prob, B, seed)
+    sys_ = [ora.local_system(frames[b], refs[b], x[b]) for b in range(B)]
+    return [np.stack([s[k] for s in sys_]) for k in range(5)]
+
+
+@pytest.mark.parametrize("name", ["quadrotor", "cartpole"])
+@pytest.mark.parametrize("eps", [1e-3, 1e-7])
+def test_qp_solution_matches_oracle(problems, native, name, eps):
+    prob, ora = problems(name)
+    hv, q, av, l, u = _qp_case(prob, ora, 21)
+    s = prob.get_settings()
+    s.eps_abs = s.eps_rel = eps
+    prob.solver.update_settings(s)
+    x, y, info = prob.solver.qp_solve_batch(hv, q, av, l, u)
+    sv = _oracle.settings_from_b200(s)
+    for b in range(hv.shape[0]):
+        ox, oy, oinfo, _ = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[b], q[b], prob.a_colptr,
+                                            prob.a_rowidx, av[b], l[b], u[b], settings=sv)
+        assert info[b, native.INFO["status"]] == oinfo[0] == native.QP_SOLVED
+        assert info[b, native.INFO["iters"]] == oinfo[1]
+        assert info[b, native.INFO["rho_updates"]] == oinfo[6]
+        assert rel_err(x[b], ox) < REL_SOLUTION
+        assert rel_err(y[b], oy) < REL_SOLUTION
+        assert abs(info[b, native.INFO["prim_res"]] - oinfo[3]) <= 1e-6 * max(1.0, abs(oinfo[3])) + 1e-9
+        assert abs(info[b, native.INFO["dual_res"]] - oinfo[4]) <= 1e-6 * max(1.0, abs(oinfo[4])) + 1e-9
+
+
+def test_admm_trace_matches_oracle(problems, native):
+    prob, ora = problems("quadrotor")
+    hv, q, av, l, u = _qp_case(prob, ora, 5, B=1)
+    s = prob.get_settings()
+    s.eps_abs = s.eps_rel = 1e-8
+    prob.solver.update_settings(s)
+    trace, x, y = prob.solver.admm_trace(hv[0], q[0], av[0], l[0], u[0])
+    ox, oy, oinfo, otrace = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[0], q[0], prob.a_colptr,
+                                             prob.a_rowidx, av[0], l[0], u[0], settings=_oracle.settings_from_b200(s))
+    assert len(trace) == len(otrace) > 1
+    assert np.array_equal(trace[:, 0], otrace[:, 0])                      # iteration numbers of the checks
+    assert np.allclose(trace[:, 3], otrace[:, 3], rtol=1e-6)              # rho schedule
+    assert np.allclose(trace[:, 1], otrace[:, 1], rtol=1e-4, atol=1e-10)  # primal residual history
+    assert np.allclose(trace[:, 2], otrace[:, 2], rtol=1e-4, atol=1e-10)  # dual residual history
+    assert np.array_equal(trace[:, 5], otrace[:, 5])
+    assert rel_err(x, ox) < REL_SOLUTION
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_preconditioners_agree(problems, native, precond):
+    prob, ora = problems("quadrotor")
+    hv, q, av, l, u = _qp_case(prob, ora, 9, B=2)
+    s = prob.get_settings()
+    s.eps_abs = s.eps_rel = 1e-6
+    s.pcg_precond = precond
+    s.pcg_max_iter = 2000
+    prob.solver.update_settings(s)
+    x, y, info = prob.solver.qp_solve_batch(hv, q, av, l, u)
+    sv = _oracle.settings_from_b200(s)
+    for b in range(2):
+        ox, oy, oinfo, _ = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[b], q[b], prob.a_colptr,
+                                            prob.a_rowidx, av[b], l[b], u[b], settings=sv)
+        assert info[b, 1] == oinfo[1]
+        assert rel_err(x[b], ox) < REL_SOLUTION
+
+
+@pytest.mark.parametrize("name,B,alpha,steps", [("quadrotor", 6, 0.1, 10), ("quadrotor", 4, 1.0, 5),
+                                                ("cartpole", 2, 0.5, 3), ("centroidal", 2, 1.0, 2)])
+def test_sqp_solve_matches_oracle(problems, native, name, B, alpha, steps):
+    prob, ora = problems(name)
+    frames, refs = prob.sample_inputs(B, 0xB200 + 2)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = alpha, steps
+    prob.solver.update_settings(s)
+    x = np.zeros((B, prob.N)); f = np.zeros(B); st = np.zeros((B, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, f, st)
+    ora.set_schedule(steps, alpha)
+    ora.set_qp_settings(_oracle.settings_from_b200(s))
+    ox, of, ost = ora.solve_batch(frames, refs)
+    assert np.array_equal(st[:, native.STAT["sqp_steps"]], ost[:, 1])
+    assert np.array_equal(st[:, native.STAT["admm_iters"]], ost[:, 2])
+    assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
+    assert rel_err(x, ox) < REL_SOLUTION
+    assert np.allclose(f, of, rtol=1e-6, atol=1e-9)
+    assert np.allclose(st[:, native.STAT["objective"]], of, rtol=1e-6, atol=1e-9)
+
+
+def test_batch_equals_single_instance(problems, native):
+    """Every instance of a batch gets the bits it gets when solved alone."""
+    prob, _ = problems("quadrotor")
+    frames, refs = prob.sample_inputs(5, 3)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = 0.5, 3
+    prob.solver.update_settings(s)
+    x = np.zeros((5, prob.N))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x)
+    for b in (0, 4):
+        xb = np.zeros((1, prob.N))
+        prob.solver.solve_batch(frames[b:b + 1], refs[b:b + 1], prob.lbx, prob.ubx, prob.lbg, prob.ubg, xb)
+        assert np.array_equal(xb[0], x[b])
+
+
+@pytest.mark.parametrize("case", [1, 2, 3, 4, 5, 6, 7])
+def test_reference_kat_cases_on_gpu(native, case):
+    """test/test.cpp:13-185 through SQPOptimizationSolver::getOptimalSolution (alpha=1, one step:
+    the cases are QPs) -- analytic optimum within the OSQP tolerance the reference runs with, and
+    the oracle's answer to 1e-6."""
+    kat = native.KatProblem(case, step_num=1, alpha=1.0)
+    x, f = kat.solve()
+    expected = _oracle.kat_expected(case)
+    assert np.abs(x - expected).max() < 5e-3
+    ox, of, _ = _oracle.kat_solve(case, 1, 1.0)
+    assert rel_err(x, ox) < REL_SOLUTION
+    s = native.default_settings()
+    s.eps_abs = s.eps_rel = 1e-9
+    s.sqp_alpha, s.sqp_step_num = 1.0, 1
+    kat2 = native.KatProblem(case, step_num=1, alpha=1.0)
+    kat2.set_settings(s)
+    x2, _ = kat2.solve()
+    assert np.abs(x2 - expected).max() < 1e-6
+
+
+def test_infeasible_qp_reports_certificate(native):
+    """x in [0,1] with the row x >= 2: primal infeasible -> status 3 and a NaN solution, which the
+    reference adds to its iterate unchecked."""
+    hc, hr = [0, 1], [0]
+    ac, ar = [0, 2], [0, 1]
+    sol = native.Solver.create(1, 2, hc, hr, ac, ar)
+    x, y, info = sol.qp_solve_batch(np.array([[1.0]]), np.array([[0.0]]), np.array([[1.0, 1.0]]),
+                                    np.array([[0.0, 2.0]]), np.array([[1.0, 3.0]]))
+    ox, oy, oinfo, _ = _oracle.qp_solve(1, 2, hc, hr, [1.0], [0.0], ac, ar, [1.0, 1.0], [0.0, 2.0], [1.0, 3.0])
+    assert info[0, 0] == oinfo[0] == native.QP_PRIMAL_INFEASIBLE
+    assert np.isnan(x).all() and np.isnan(ox).all()
+
+
+def test_class_api_single_instance(problems, native):
+    """OptimalControlProblem::computeOptimalTrajectory: pins the first frame, warm-starts the next call."""
+    prob = native.Problem("quadrotor", alpha=1.0, step_num=4)
+    ora = _oracle.OracleProblem("quadrotor", alpha=1.0, step_num=4)
+    frames, refs = prob.sample_inputs(1, 99)
+    x1, f1 = prob.compute_optimal_trajectory(frames[0], refs[0])
+    ox1, of1, _ = ora.solve_batch(frames, refs)
+    assert rel_err(x1, ox1[0]) < REL_SOLUTION
+    assert abs(x1[:prob.nf] - frames[0]).max() < 1e-3          # first frame pinned (to OSQP tolerance)
+    x2, f2 = prob.compute_optimal_trajectory(frames[0], refs[0])  # continues from x1
+    ox2, of2, _ = ora.solve_batch(frames, refs, x0=ox1)
+    assert rel_err(x2, ox2[0]) < REL_SOLUTION
+    assert f2 <= f1 + 1e-6
