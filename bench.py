@@ -145,13 +145,26 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------
-def algorithmic_bytes(dims, nnz_pu, stats, ocp):
-    """SURVEY.md §8d, summed over the instances of one batched solve (all its SQP steps)."""
+def algorithmic_bytes(dims, nnz_pu, stats, ocp, direct=None):
+    """Bytes one batched solve (all its SQP steps) has to move if every operand of every
+    operation is streamed once (no credit for shared-memory residency), from the per-instance
+    iteration counts in the stats buffer.  PCG kernel: SURVEY.md §8d.  Direct kernel
+    (DESIGN.md §5): per ADMM iteration the rhs build and the fused update read A once each,
+    the block-tridiagonal solve reads D^-1 once and L, L_p twice (forward + backward sweep)."""
     n, m, nnz_a = dims["n"], dims["m"], dims["nnz_a"]
     iters = stats[:, ocp.STAT["admm_iters"]].sum()
     pcg = stats[:, ocp.STAT["pcg_iters"]].sum()
     checks = stats[:, ocp.STAT["checks"]].sum()
     mat = nnz_pu + 2 * nnz_a
+    if direct is not None:
+        np_, bs, nb = direct["np"], direct["bs"], direct["nb"]
+        fac = nb * bs * bs + 2 * (nb - 1) * bs * bs + 2 * np_ * nb * bs + np_ * np_
+        per_iter = 8.0 * (2 * nnz_a + fac + 10 * n + 9 * m)
+        qps = stats[:, ocp.STAT["sqp_steps"]].sum()
+        setup = 8.0 * ((nnz_a + nnz_pu + n + 2 * m) + 10 * 3 * (2 * nnz_pu + nnz_a) + 4 * fac)
+        check = 8.0 * checks * (mat + 4 * n + 4 * m)
+        return iters * per_iter + qps * setup + check, dict(admm_iters=float(iters), kkt_solves=float(pcg),
+                                                            checks=float(checks), qps=float(qps))
     admm = 8.0 * ((pcg + iters) * mat + iters * (2 * nnz_a + 8 * n + 12 * m) + pcg * (6 * n + 2 * m))
     check = 8.0 * checks * (mat + 4 * n + 4 * m)
     return admm + check, dict(admm_iters=float(iters), pcg_iters=float(pcg), checks=float(checks))
@@ -240,7 +253,12 @@ def b200_arm(args):
 
     stats_h = d_stats.cpu().numpy()
     solved = int((stats_h[:, ocp.STAT["qp_status"]] == ocp.QP_SOLVED).sum())
-    bytes_per_solve_call, counts = algorithmic_bytes(dims, nnz_pu, stats_h, ocp)
+    dd = sol.device_dims()
+    direct = None
+    if dd["resident"] & 2:
+        G = max(g for g in range(1, prob.horizon + 1) if prob.horizon % g == 0 and (g * prob.nf <= 20 or g == 1))
+        direct = dict(np=prob.np_, bs=G * prob.nf, nb=prob.horizon // G)
+    bytes_per_solve_call, counts = algorithmic_bytes(dims, nnz_pu, stats_h, ocp, direct)
     admm_ms_per_launch = prof["admm"]["ms"] / max(1, prof["admm"]["launches"])
     bytes_per_launch = bytes_per_solve_call / STEP_NUM
     achieved = bytes_per_launch / (admm_ms_per_launch * 1e-3) / 1e9 if admm_ms_per_launch > 0 else 0.0
@@ -323,7 +341,7 @@ def b200_arm(args):
                 "clocks": clocks,
                 "latency_p50_ms": float(np.median(lat)) if lat else None,
                 "solved_fraction": solved / B,
-                "device": torch.cuda.get_device_name(local), "resident": sol.device_dims()}
+                "device": torch.cuda.get_device_name(local), "kernel_plan": dict(dd, linsys="block-tridiagonal LDL' (direct)" if direct else "PCG")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

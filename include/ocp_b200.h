@@ -42,10 +42,15 @@ extern "C" {
 #define OCP_B200_QP_MAX_ITER_REACHED     7
 #define OCP_B200_QP_UNSOLVED            11
 
-/* ---- PCG preconditioners ------------------------------------------------ */
-#define OCP_B200_PRECOND_DIAGONAL      0  /* Jacobi, what OSQP's cuda backend ships */
-#define OCP_B200_PRECOND_BLOCK_JACOBI  1  /* one dense block per stage (+ one for p) */
-#define OCP_B200_PRECOND_BLOCK_TRIDIAG 2  /* stage-block tridiagonal Cholesky        */
+/* ---- reduced-KKT linear system (K = P + sigma I + A' diag(rho) A) ------- */
+#define OCP_B200_PRECOND_DIAGONAL      0  /* PCG, Jacobi: what OSQP's cuda backend ships       */
+#define OCP_B200_PRECOND_BLOCK_JACOBI  1  /* PCG, one dense block per stage (+ one for p)      */
+#define OCP_B200_PRECOND_BLOCK_TRIDIAG 2  /* stage-block tridiagonal LDL' with a dense border
+                                           * for p.  K of a multiple-shooting OCP has exactly
+                                           * this structure, so the factorisation IS K and one
+                                           * application solves the system (no CG iterations).
+                                           * Patterns without that structure fall back to
+                                           * BLOCK_JACOBI PCG (see ocp_b200_get_dims).        */
 
 /* Settings.  Defaults (ocp_b200_default_settings) are the values the reference
  * runs with: SQPOptimizationSolver.cpp:81-85 (eps 1e-3, max_iter 10000), the OSQP
@@ -192,8 +197,22 @@ long long ocp_b200_launch_count(const ocp_b200_solver* s);
 #define OCP_B200_PROF_ASSEMBLE  1  /* stage-library assembly kernel                 */
 #define OCP_B200_PROF_OBJECTIVE 2  /* objective + stats store                       */
 int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled);
+/* While profiling is on, CTA 0 of the direct kernel also accumulates SM cycles per phase of the
+ * QP solves it runs (clock64 on one thread); get_phase_cycles returns and clears them. */
+#define OCP_B200_NPHASE 8
+#define OCP_B200_PHASE_LOAD         0
+#define OCP_B200_PHASE_SCALE        1  /* Ruiz equilibration                        */
+#define OCP_B200_PHASE_KKT_ASSEMBLE 2  /* K = P + sigma I + A' rho A into blocks    */
+#define OCP_B200_PHASE_FACTOR       3  /* block-tridiagonal LDL'                    */
+#define OCP_B200_PHASE_RHS          4
+#define OCP_B200_PHASE_SOLVE        5
+#define OCP_B200_PHASE_UPDATE       6  /* z~ = A x~, relaxation, projection, duals  */
+#define OCP_B200_PHASE_CHECK        7  /* residuals, termination, rho adaptation    */
+int ocp_b200_get_phase_cycles(ocp_b200_solver* s, long long* cycles);
 int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int reset);
-/* dimensions of a handle: n, m, nnz_h, nnz_a, shared memory bytes per instance, resident (1) or streaming (0) */
+/* dimensions of a handle: n, m, nnz_h, nnz_a, dynamic shared memory bytes per CTA, and
+ * resident: bit 0 = all per-instance state is in shared memory, bit 1 = the direct
+ * block-tridiagonal kernel is in use (0 = PCG kernel) */
 int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int* nnz_a,
                       int* smem_bytes, int* resident);
 

@@ -118,6 +118,7 @@ def cuda_lib() -> C.CDLL:
         lib.ocp_b200_get_dims.argtypes = [vptr] + [C.POINTER(C.c_int)] * 6
         lib.ocp_b200_set_profiling.argtypes = [vptr, C.c_int]
         lib.ocp_b200_get_profile.argtypes = [vptr, dptr, C.POINTER(C.c_longlong), C.c_int]
+        lib.ocp_b200_get_phase_cycles.argtypes = [vptr, C.POINTER(C.c_longlong)]
         _cuda = lib
     return _cuda
 
@@ -255,6 +256,12 @@ class Solver:
         ms = (C.c_double * 3)(); cnt = (C.c_longlong * 3)()
         _check(cuda_lib().ocp_b200_get_profile(self._h, ms, cnt, int(reset)))
         return {k: dict(ms=ms[i], launches=cnt[i]) for i, k in enumerate(("admm", "assemble", "objective"))}
+
+    def get_phase_cycles(self) -> dict:
+        """SM cycles per QP phase accumulated by CTA 0 of the direct kernel while profiling was on."""
+        c = (C.c_longlong * 8)()
+        _check(cuda_lib().ocp_b200_get_phase_cycles(self._h, c))
+        return dict(zip(("load", "scale", "kkt_assemble", "factor", "rhs", "solve", "update", "check"), list(c)))
 
     def device_dims(self) -> dict:
         v = [C.c_int() for _ in range(6)]

@@ -88,13 +88,28 @@ def compile_objects(sources: list[str], flags: list[str], objdir: Path, tag: str
     return objs
 
 
+CUDA_SOURCES = ["csrc/ocp_b200.cu", "csrc/direct_smem.cu", "csrc/direct_mixed.cu"]
+NVCC_FLAGS = [*ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + str(INCLUDE), "-I" + str(PKG / "csrc")]
+
+
 def build_cuda(force: bool = False) -> Path:
+    """nvcc -c every CUDA translation unit (in parallel), then link libocp_b200.so."""
     LIB.mkdir(parents=True, exist_ok=True)
+    OBJ.mkdir(parents=True, exist_ok=True)
     out = LIB / "libocp_b200.so"
-    deps = [PKG / "csrc/ocp_b200.cu", PKG / "csrc/admm_kernel.cuh", INCLUDE / "ocp_b200.h", INCLUDE / "ocp_b200_model.h"]
-    if force or _stale(out, deps):
-        _run([NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-I" + str(INCLUDE),
-              "-I" + str(PKG / "csrc"), "-o", str(out), str(PKG / "csrc/ocp_b200.cu"), "-ldl"])
+    deps = [*(PKG / "csrc").glob("*.cuh"), *(PKG / "csrc").glob("*.h"), INCLUDE / "ocp_b200.h", INCLUDE / "ocp_b200_model.h"]
+    jobs, objs = [], []
+    for src in CUDA_SOURCES:
+        sp = PKG / src
+        op = OBJ / (sp.stem + ".cu.o")
+        objs.append(op)
+        if force or _stale(op, [sp] + deps):
+            jobs.append([NVCC, *NVCC_FLAGS, "-c", str(sp), "-o", str(op)])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            list(ex.map(_run, jobs))
+    if force or _stale(out, objs):
+        _run([NVCC, *ARCH, "-shared", "-o", str(out), *map(str, objs), "-ldl"])
     return out
 
 

@@ -1,0 +1,699 @@
+// admm_direct_kernel.cuh -- batched ADMM QP solver for sm_100a with a DIRECT reduced-KKT solve.
+//
+// Replaces, for B independent QPs that share one sparsity pattern, what the reference does per
+// SQP step through OsqpEigen/OSQP (src/sqp_solver/CuCaQP.cpp:271-288, 183-224): osqp_setup
+// (bound clamping, Ruiz equilibration x10 with cost normalisation, rho vector, factorisation,
+// cold start) and osqp_solve (ADMM iterations, residual / termination / infeasibility checks
+// every 25 iterations, adaptive rho, unscaling), then the SQP update x += alpha * d[np:]
+// (SQPOptimizationSolver.cpp:171-177).
+//
+// Linear system.  OSQP's reduced ("indirect") KKT matrix
+//     K = P + sigma I + A' diag(rho) A
+// of a multiple-shooting OCP is block tridiagonal in the stage index (dynamics rows couple
+// stage k with k+1 only) with a dense border for the reference parameters p, which every
+// stage cost may touch.  With the p columns ordered last, K = L D L' with dense bs x bs
+// blocks has no fill outside that structure:
+//     D_k   = K_kk - L_k D_{k-1} L_k'            L_k   = K_{k,k-1} D_{k-1}^-1
+//     V_k   = K_pk - V_{k-1} L_k'                L_pk  = V_k D_k^-1
+//     D_p   = K_pp - sum_k V_k L_pk'
+// The kernel keeps D_k^-1 (explicit, Gauss-Jordan), L_k and L_pk, so that a solve is two
+// sequential sweeps of dense bs x bs mat-vecs (one warp) plus fully parallel dense work.  The
+// solve is exact up to rounding, like the LDL' of the full KKT system that the reference's CPU
+// build of OSQP uses (oracle/osqp_restate.hpp) -- the ADMM iterates of the two agree to
+// rounding, which is what the parity tests check.
+//
+// Layout.  One persistent CTA per SM takes instances from an atomic counter.  Per-instance
+// state is a list of arrays (vectors, matrix values, factor blocks, index structures); a
+// host-side plan puts as many of them as fit into shared memory, in priority order, and the
+// rest into a per-CTA slab of global memory that stays L2-resident.  For the H=20 quadrotor
+// everything is in shared memory and an ADMM iteration touches no DRAM at all.  Termination,
+// rho updates and refactorisations are decided on the device: one launch per SQP step.
+#pragma once
+
+#include "admm_common.cuh"
+
+namespace ocpb200 {
+namespace direct {
+
+constexpr int kDirectThreads = 256;   // 255 registers per thread: the unrolled block code does not spill
+
+// arrays of the per-instance state, in shared-memory priority order
+enum ArrayId {
+  AR_X = 0, AR_Q, AR_B, AR_Z, AR_Y, AR_L, AR_U, AR_CTYPE, AR_AVAL, AR_DINV, AR_LSUB, AR_IDX, AR_PVAL, AR_BORDER,
+  AR_D, AR_E, AR_DX, AR_DY, AR_COUNT
+};
+
+struct Work {
+  double *x, *q, *b, *z, *y, *l, *u;
+  signed char* ctype;
+  double *Aval, *Dinv, *Lsub;
+  idx_t* idx;
+  double *Pval;
+  double *Lp, *Dp, *S, *Sp, *xp, *piv;   // border: L_pk [np x N], D_p^-1 [np x (np+1)], scratch blocks
+  double *D, *E, *dx, *dy;
+};
+
+__host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
+  const size_t n = P.n, m = P.m, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb, np = P.tri_np;
+  switch (id) {
+    case AR_X: case AR_Q: case AR_B: case AR_D: case AR_DX: return (n + 1) & ~size_t(1);
+    case AR_Z: case AR_Y: case AR_L: case AR_U: case AR_E: case AR_DY: return (m + 1) & ~size_t(1);
+    case AR_CTYPE: return (m + 7) / 8;
+    case AR_AVAL: return (size_t(P.nnz_a) + 1) & ~size_t(1);
+    case AR_PVAL: return (size_t(P.nnz_p) + 1) & ~size_t(1);
+    case AR_DINV: case AR_LSUB: return nb * bs * ld;
+    case AR_IDX: return (size_t(P.idx_entries) * sizeof(idx_t) + 7) / 8;
+    case AR_BORDER: return ((np * nb * bs + 1) & ~size_t(1)) + np * (np + 1) + ((bs * ld + 1) & ~size_t(1)) +
+                           ((np * bs + 1) & ~size_t(1)) + ((np + 2) & ~size_t(1)) + 66;
+    default: return 0;
+  }
+}
+
+__host__ __device__ inline size_t slab_doubles_for(const PatternDev& P, uint32_t smem_mask) {
+  size_t tot = 0;
+  for (int id = 0; id < AR_COUNT; ++id)
+    if (!(smem_mask >> id & 1u)) tot += (array_doubles(P, id) + 1) & ~size_t(1);
+  return tot;
+}
+
+// kAllSmem: every array is in shared memory (the plan's mask has all bits set); the pointers are
+// then derived from the shared-memory base only, which lets the compiler emit LDS/STS.
+template <bool kAllSmem>
+__device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t smem_mask, double* sm, double* gl) {
+  double* ptr[AR_COUNT];
+#pragma unroll
+  for (int id = 0; id < AR_COUNT; ++id) {
+    const size_t sz = (array_doubles(P, id) + 1) & ~size_t(1);
+    if (kAllSmem || (smem_mask >> id & 1u)) { ptr[id] = sm; sm += sz; }
+    else { ptr[id] = gl; gl += sz; }
+  }
+  W.x = ptr[AR_X]; W.q = ptr[AR_Q]; W.b = ptr[AR_B]; W.z = ptr[AR_Z]; W.y = ptr[AR_Y]; W.l = ptr[AR_L]; W.u = ptr[AR_U];
+  W.ctype = reinterpret_cast<signed char*>(ptr[AR_CTYPE]);
+  W.Aval = ptr[AR_AVAL]; W.Dinv = ptr[AR_DINV]; W.Lsub = ptr[AR_LSUB];
+  W.idx = reinterpret_cast<idx_t*>(ptr[AR_IDX]);
+  W.Pval = ptr[AR_PVAL];
+  const size_t np = P.tri_np, N = size_t(P.tri_nb) * P.tri_bs;
+  double* bp = ptr[AR_BORDER];
+  W.Lp = bp; bp += (np * N + 1) & ~size_t(1);
+  W.Dp = bp; bp += np * (np + 1);
+  W.S = bp; bp += (size_t(P.tri_bs) * P.tri_ld + 1) & ~size_t(1);
+  W.Sp = bp; bp += (np * P.tri_bs + 1) & ~size_t(1);
+  W.xp = bp; bp += (np + 2) & ~size_t(1);
+  W.piv = bp;
+  W.D = ptr[AR_D]; W.E = ptr[AR_E]; W.dx = ptr[AR_DX]; W.dy = ptr[AR_DY];
+}
+
+struct Rho {
+  double ineq, eq, inv_ineq, inv_eq;
+  __device__ explicit Rho(double rho) : ineq(rho), eq(kRhoEqOverIneq * rho), inv_ineq(1.0 / rho), inv_eq(1.0 / (kRhoEqOverIneq * rho)) {}
+  __device__ __forceinline__ double of(signed char ct) const { return ct == 1 ? eq : (ct == -1 ? kRhoMin : ineq); }
+  __device__ __forceinline__ double inv(signed char ct) const { return ct == 1 ? inv_eq : (ct == -1 ? 1.0 / kRhoMin : inv_ineq); }
+};
+
+// ---------------------------------------------------------------------------------------
+// K -> factor storage: Dinv_k <- K_kk, Lsub_k <- K_{k,k-1}, Lp <- K_p., Dp <- K_pp
+// entry (i, j) = [i == j] sigma + P_ij + sum_r rho_r A_ri A_rj  (sorted merge of two columns)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double k_entry(const PatternDev& P, const Work& W, const Rho& rho, double sigma, int i, int j) {
+  double s = (i == j) ? sigma : 0.0;
+  {
+    const int e = P.p_colptr[j + 1];
+    for (int k = P.p_colptr[j]; k < e; ++k)
+      if (P.p_rowidx[k] == i) { s += W.Pval[k]; break; }
+  }
+  int ka = P.a_colptr[i], kc = P.a_colptr[j];
+  const int ea = P.a_colptr[i + 1], ec = P.a_colptr[j + 1];
+  if (ka < ea && kc < ec) {
+    int ra = P.a_rowidx[ka], rc = P.a_rowidx[kc];
+    while (true) {
+      if (ra == rc) {
+        s += rho.of(W.ctype[ra]) * W.Aval[ka] * W.Aval[kc];
+        if (++ka >= ea || ++kc >= ec) break;
+        ra = P.a_rowidx[ka]; rc = P.a_rowidx[kc];
+      } else if (ra < rc) {
+        if (++ka >= ea) break;
+        ra = P.a_rowidx[ka];
+      } else {
+        if (++kc >= ec) break;
+        rc = P.a_rowidx[kc];
+      }
+    }
+  }
+  return s;
+}
+
+__device__ inline void tri_assemble(const PatternDev& P, const Work& W, const Rho& rho, double sigma) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
+  const int bb = bs * bs;
+  // diagonal blocks: upper triangle computed, mirrored
+  for (int e = tid; e < nb * bb; e += T) {
+    const int k = e / bb, r = (e - k * bb) / bs, c = e - k * bb - r * bs;
+    if (r > c) continue;
+    const double v = k_entry(P, W, rho, sigma, np + k * bs + r, np + k * bs + c);
+    double* Dk = W.Dinv + size_t(k) * bs * ld;
+    Dk[r * ld + c] = v;
+    Dk[c * ld + r] = v;
+  }
+  // sub-diagonal blocks K_{k,k-1}
+  for (int e = tid; e < (nb - 1) * bb; e += T) {
+    const int k = 1 + e / bb, r = (e - (k - 1) * bb) / bs, c = e - (k - 1) * bb - r * bs;
+    W.Lsub[size_t(k) * bs * ld + r * ld + c] = k_entry(P, W, rho, sigma, np + k * bs + r, np + (k - 1) * bs + c);
+  }
+  // border rows
+  for (int e = tid; e < np * N; e += T) {
+    const int r = e / N, j = e - r * N;
+    W.Lp[size_t(r) * N + j] = k_entry(P, W, rho, sigma, r, np + j);
+  }
+  for (int e = tid; e < np * np; e += T) {
+    const int r = e / np, c = e - r * np;
+    if (r > c) continue;
+    const double v = k_entry(P, W, rho, sigma, r, c);
+    W.Dp[r * (np + 1) + c] = v;
+    W.Dp[c * (np + 1) + r] = v;
+  }
+  __syncthreads();
+}
+
+// in-place Gauss-Jordan inverse of an SPD block (no pivoting), executed by ONE warp
+__device__ __forceinline__ void warp_invert(double* M, int bs, int ld, int lane) {
+  for (int k = 0; k < bs; ++k) {
+    const double ipiv = 1.0 / M[k * ld + k];
+    __syncwarp();
+    for (int c = lane; c < bs; c += 32) M[k * ld + c] = (c == k) ? ipiv : M[k * ld + c] * ipiv;
+    __syncwarp();
+    for (int idx = lane; idx < bs * bs; idx += 32) {
+      const int r = idx / bs, c = idx - r * bs;
+      if (r != k && c != k) M[r * ld + c] -= M[r * ld + k] * M[k * ld + c];
+    }
+    __syncwarp();
+    for (int r = lane; r < bs; r += 32)
+      if (r != k) M[r * ld + k] = -M[r * ld + k] * ipiv;
+    __syncwarp();
+  }
+}
+
+// block LDL' of the bordered block-tridiagonal K held in the factor storage
+__device__ inline void tri_factor(const PatternDev& P, const Work& W) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
+  const int bb = bs * bs;
+  for (int k = 0; k < nb; ++k) {
+    double* Dk = W.Dinv + size_t(k) * bs * ld;
+    if (k > 0) {
+      double* Tk = W.Lsub + size_t(k) * bs * ld;               // K_{k,k-1}
+      const double* Dm = W.Dinv + size_t(k - 1) * bs * ld;     // D_{k-1}^-1
+      // S = K_{k,k-1} D_{k-1}^-1  (= L_k);  Sp = V_{k-1}
+      for (int e = tid; e < bb; e += T) {
+        const int r = e / bs, c = e - r * bs;
+        double s = 0.0;
+        for (int t = 0; t < bs; ++t) s += Tk[r * ld + t] * Dm[t * ld + c];
+        W.S[r * ld + c] = s;
+      }
+      for (int e = tid; e < np * bs; e += T) {
+        const int r = e / bs, c = e - r * bs;
+        W.Sp[e] = W.Lp[size_t(r) * N + (k - 1) * bs + c];
+      }
+      __syncthreads();
+      // D_k = K_kk - S K_{k,k-1}';  V_k = K_pk - V_{k-1} S';  L_{p,k-1} = V_{k-1} D_{k-1}^-1
+      for (int e = tid; e < bb; e += T) {
+        const int r = e / bs, c = e - r * bs;
+        double s = 0.0;
+        for (int t = 0; t < bs; ++t) s += W.S[r * ld + t] * Tk[c * ld + t];
+        Dk[r * ld + c] -= s;
+      }
+      for (int e = tid; e < np * bs; e += T) {
+        const int r = e / bs, c = e - r * bs;
+        double s = 0.0, f = 0.0;
+        for (int t = 0; t < bs; ++t) {
+          const double v = W.Sp[r * bs + t];
+          s += v * W.S[c * ld + t];
+          f += v * Dm[t * ld + c];
+        }
+        W.Lp[size_t(r) * N + k * bs + c] -= s;
+        W.Lp[size_t(r) * N + (k - 1) * bs + c] = f;
+      }
+      __syncthreads();
+      // D_p -= V_{k-1} L_{p,k-1}';  L_k <- S
+      for (int e = tid; e < np * np; e += T) {
+        const int r = e / np, c = e - r * np;
+        double s = 0.0;
+        for (int t = 0; t < bs; ++t) s += W.Sp[r * bs + t] * W.Lp[size_t(c) * N + (k - 1) * bs + t];
+        W.Dp[r * (np + 1) + c] -= s;
+      }
+      for (int e = tid; e < bb; e += T) {
+        const int r = e / bs, c = e - r * bs;
+        Tk[r * ld + c] = W.S[r * ld + c];
+      }
+    }
+    if (warp == 0) warp_invert(Dk, bs, ld, lane);
+    __syncthreads();
+  }
+  // last border block, then D_p^-1
+  if (np > 0) {
+    const double* Dm = W.Dinv + size_t(nb - 1) * bs * ld;
+    for (int e = tid; e < np * bs; e += T) {
+      const int r = e / bs, c = e - r * bs;
+      W.Sp[e] = W.Lp[size_t(r) * N + (nb - 1) * bs + c];
+    }
+    __syncthreads();
+    for (int e = tid; e < np * bs; e += T) {
+      const int r = e / bs, c = e - r * bs;
+      double f = 0.0;
+      for (int t = 0; t < bs; ++t) f += W.Sp[r * bs + t] * Dm[t * ld + c];
+      W.Lp[size_t(r) * N + (nb - 1) * bs + c] = f;
+    }
+    __syncthreads();
+    for (int e = tid; e < np * np; e += T) {
+      const int r = e / np, c = e - r * np;
+      double s = 0.0;
+      for (int t = 0; t < bs; ++t) s += W.Sp[r * bs + t] * W.Lp[size_t(c) * N + (nb - 1) * bs + t];
+      W.Dp[r * (np + 1) + c] -= s;
+    }
+    __syncthreads();
+    if (warp == 0) warp_invert(W.Dp, np, np + 1, lane);
+    __syncthreads();
+  }
+}
+
+// K x = b in place: b is [p | block 0 | ... | block nb-1]
+__device__ inline void tri_solve(const PatternDev& P, const Work& W) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
+  double* bx = W.b + np;
+  // forward sweep: y_k = b_k - L_k y_{k-1}   (one warp; lanes own rows)
+  if (warp == 0) {
+    for (int k = 1; k < nb; ++k) {
+      const double* Lk = W.Lsub + size_t(k) * bs * ld;
+      const double* yp = bx + (k - 1) * bs;
+      double* yk = bx + k * bs;
+      for (int r = lane; r < bs; r += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        int c = 0;
+        for (; c + 1 < bs; c += 2) { s0 += Lk[r * ld + c] * yp[c]; s1 += Lk[r * ld + c + 1] * yp[c + 1]; }
+        if (c < bs) s0 += Lk[r * ld + c] * yp[c];
+        yk[r] -= s0 + s1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // border: y_p = b_p - sum_k L_pk y_k  (a warp per border row), x_p = D_p^-1 y_p
+  if (np > 0) {
+    for (int r = warp; r < np; r += nw) {
+      double s = 0.0;
+      const double* row = W.Lp + size_t(r) * N;
+      for (int j = lane; j < N; j += 32) s += row[j] * bx[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) W.xp[r] = W.b[r] - s;
+    }
+    __syncthreads();
+    if (tid < np) {
+      double s = 0.0;
+      for (int c = 0; c < np; ++c) s += W.Dp[tid * (np + 1) + c] * W.xp[c];
+      W.b[tid] = s;
+    }
+    __syncthreads();
+  }
+  // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
+  const int Tb = (T / bs) * bs;   // whole blocks per pass: a pass never reads what it overwrites
+  for (int base = 0; base < N; base += Tb) {
+    const int j = tid < Tb ? base + tid : N;
+    double v = 0.0;
+    if (j < N) {
+      const int k = j / bs, r = j - k * bs;
+      const double* Dk = W.Dinv + size_t(k) * bs * ld + r * ld;
+      const double* yk = bx + k * bs;
+      double s0 = 0.0, s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < bs; c += 2) { s0 += Dk[c] * yk[c]; s1 += Dk[c + 1] * yk[c + 1]; }
+      if (c < bs) s0 += Dk[c] * yk[c];
+      v = s0 + s1;
+      for (int p = 0; p < np; ++p) v -= W.Lp[size_t(p) * N + j] * W.b[p];
+    }
+    __syncthreads();
+    if (j < N) bx[j] = v;
+  }
+  __syncthreads();
+  // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}
+  if (warp == 0) {
+    for (int k = nb - 2; k >= 0; --k) {
+      const double* Ln = W.Lsub + size_t(k + 1) * bs * ld;
+      const double* xn = bx + (k + 1) * bs;
+      double* xk = bx + k * bs;
+      for (int r = lane; r < bs; r += 32) {
+        double s0 = 0.0, s1 = 0.0;
+        int c = 0;
+        for (; c + 1 < bs; c += 2) { s0 += Ln[c * ld + r] * xn[c]; s1 += Ln[(c + 1) * ld + r] * xn[c + 1]; }
+        if (c < bs) s0 += Ln[c * ld + r] * xn[c];
+        xk[r] -= s0 + s1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace direct
+}  // namespace ocpb200
+#include "tri_fast.cuh"
+namespace ocpb200 {
+namespace direct {
+
+// block-size dispatch (uniform across the CTA)
+__device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work& W) {
+  if (P.tri_bs == 16) tri_factor_exact<16>(P, W);
+  else if (P.tri_bs == 20) tri_factor_exact<20>(P, W);
+  else tri_factor(P, W);
+}
+__device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
+  if (P.tri_bs == 16) tri_solve_exact<16>(P, W);
+  else if (P.tri_bs == 20) tri_solve_exact<20>(P, W);
+  else tri_solve(P, W);
+}
+
+// ---------------------------------------------------------------------------------------
+// one QP, solved by the whole CTA
+// ---------------------------------------------------------------------------------------
+__device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settings& S, const SolveArgs& A,
+                                      const Work& W, Reducer& R, int inst, QpResult& out) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = P.n, m = P.m;
+  const double sigma = S.sigma, relax = S.relax;
+  PhaseClock clk(A.phase);
+
+  // ---- load (osqp_setup copies its inputs): values, q, bounds clamped to +-1e30 ------------
+  {
+    const double* hv = A.h_vals + size_t(inst) * A.ld_h;
+    const double* av = A.a_vals + size_t(inst) * A.ld_a;
+    const double* qv = A.q + size_t(inst) * A.ld_n;
+    const double* lv = A.l + size_t(inst) * A.ld_m;
+    const double* uv = A.u + size_t(inst) * A.ld_m;
+    for (int k = tid; k < P.nnz_a; k += T) W.Aval[k] = av[k];
+    for (int k = tid; k < P.nnz_p; k += T) { const int s = P.p_src[k]; W.Pval[k] = s >= 0 ? hv[s] : 0.0; }
+    for (int j = tid; j < n; j += T) { W.q[j] = qv[j]; W.D[j] = 1.0; W.x[j] = 0.0; }
+    double bad[1] = {0.0};
+    for (int i = tid; i < m; i += T) {
+      const double lo = lv[i], hi = uv[i];
+      if (lo > hi) bad[0] = 1.0;
+      W.l[i] = fmax(lo, -kInfty);
+      W.u[i] = fmin(hi, kInfty);
+      W.E[i] = 1.0; W.z[i] = 0.0; W.y[i] = 0.0;
+    }
+    block_reduce<1, true>(bad, R);
+    if (bad[0] > 0.0) {  // osqp_setup rejects l > u; the reference then adds no usable step
+      out = QpResult{OCP_B200_QP_UNSOLVED, 0, 0, 0, 0, 0.0, 0.0, S.rho};
+      return;
+    }
+  }
+
+  clk.lap(OCP_B200_PHASE_LOAD);
+  // ---- Ruiz equilibration (scale_data): D, E, c;  scratch: b (n), dy (m) ---------------------
+  double c = 1.0;
+  for (int pass = 0; pass < S.scaling_iters; ++pass) {
+    for (int j = tid; j < n; j += T) {
+      double dn = 0.0;
+      for (int k = P.p_colptr[j]; k < P.p_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Pval[k]));
+      for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Aval[k]));
+      W.b[j] = 1.0 / sqrt(limit_scaling(dn));
+    }
+    for (int i = tid; i < m; i += T) {
+      double en = 0.0;
+      for (int k = P.a_rowptr[i]; k < P.a_rowptr[i + 1]; ++k) en = fmax(en, fabs(W.Aval[P.a_perm[k]]));
+      W.dy[i] = 1.0 / sqrt(limit_scaling(en));
+    }
+    __syncthreads();
+    double red[2] = {0.0, 0.0};  // sum of P column norms, max |q|
+    for (int j = tid; j < n; j += T) {
+      const double dj = W.b[j];
+      double cn = 0.0;
+      for (int k = P.p_colptr[j]; k < P.p_colptr[j + 1]; ++k) {
+        const double v = W.Pval[k] * W.b[P.p_rowidx[k]] * dj;
+        W.Pval[k] = v;
+        cn = fmax(cn, fabs(v));
+      }
+      for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) W.Aval[k] *= W.dy[P.a_rowidx[k]] * dj;
+      const double qj = W.q[j] * dj;
+      W.q[j] = qj;
+      W.D[j] *= dj;
+      red[0] += cn;
+      red[1] = fmax(red[1], fabs(qj));
+    }
+    for (int i = tid; i < m; i += T) W.E[i] *= W.dy[i];
+    double sum[1] = {red[0]}, mx[1] = {red[1]};
+    block_reduce<1, false>(sum, R);
+    block_reduce<1, true>(mx, R);
+    const double ct = 1.0 / limit_scaling(fmax(sum[0] / double(n), limit_scaling(mx[0])));
+    for (int k = tid; k < P.nnz_p; k += T) W.Pval[k] *= ct;
+    for (int j = tid; j < n; j += T) W.q[j] *= ct;
+    c *= ct;
+    __syncthreads();
+  }
+  const double cinv = 1.0 / c;
+
+  // ---- scaled bounds, constraint types (set_rho_vec) ------------------------------------------
+  double rho = fmin(fmax(S.rho, kRhoMin), kRhoMax);
+  for (int i = tid; i < m; i += T) {
+    const double lo = W.l[i] * W.E[i], hi = W.u[i] * W.E[i];
+    W.l[i] = lo; W.u[i] = hi;
+    signed char ct = 0;
+    if (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ct = -1;
+    else if (hi - lo < kRhoTol) ct = 1;
+    W.ctype[i] = ct;
+  }
+  __syncthreads();
+  Rho rv(rho);
+  clk.lap(OCP_B200_PHASE_SCALE);
+  tri_assemble(P, W, rv, sigma);
+  clk.lap(OCP_B200_PHASE_KKT_ASSEMBLE);
+  factor_dispatch(P, W);
+  clk.lap(OCP_B200_PHASE_FACTOR);
+
+  const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : 4 * S.check_termination;
+  int status = OCP_B200_QP_UNSOLVED, iter = 0, solves = 0, rho_updates = 0, checks = 0, n_trace = 0;
+  double prim_res = 0.0, dual_res = 0.0;
+  bool done = false;
+
+  for (iter = 1; iter <= S.admm_max_iter && !done; ++iter) {
+    // ---- right-hand side of the reduced KKT system: sigma x - q + A'(rho z - y) --------------
+    for (int j = tid; j < n; j += T) {
+      double s = sigma * W.x[j] - W.q[j];
+      const int e = P.a_colptr[j + 1];
+      for (int k = P.a_colptr[j]; k < e; ++k) {
+        const int r = P.a_rowidx[k];
+        s += W.Aval[k] * (rv.of(W.ctype[r]) * W.z[r] - W.y[r]);
+      }
+      W.b[j] = s;
+    }
+    __syncthreads();
+    clk.lap(OCP_B200_PHASE_RHS);
+    solve_dispatch(P, W);   // b <- x~
+    ++solves;
+    clk.lap(OCP_B200_PHASE_SOLVE);
+
+    // ---- x, z, y updates with relaxation and projection (update_x / update_z / update_y) ----
+    const bool can_check = S.check_termination > 0 && (iter % S.check_termination == 0);
+    const bool last_iter = iter == S.admm_max_iter;
+    const bool rho_time = S.adaptive_rho && rho_interval > 0 && (iter % rho_interval == 0);
+    const bool want_info = can_check || rho_time || last_iter;
+    for_rows_A(P, W.Aval, W.b, [&](int i, double zt) {
+      const signed char ct = W.ctype[i];
+      const double rh = rv.of(ct);
+      const double zr = relax * zt + (1.0 - relax) * W.z[i];
+      const double zn = fmin(fmax(zr + rv.inv(ct) * W.y[i], W.l[i]), W.u[i]);
+      const double dy = rh * (zr - zn);
+      W.y[i] += dy;
+      W.z[i] = zn;
+      if (want_info) W.dy[i] = dy;
+    });
+    for (int j = tid; j < n; j += T) {
+      const double xo = W.x[j];
+      const double xn = relax * W.b[j] + (1.0 - relax) * xo;
+      if (want_info) W.dx[j] = xn - xo;
+      W.x[j] = xn;
+    }
+    __syncthreads();
+    clk.lap(OCP_B200_PHASE_UPDATE);
+    if (!want_info) continue;
+
+    // ---- update_info: residuals of the unscaled problem ------------------------------------
+    ++checks;
+    double mx[kRedWidth];
+#pragma unroll
+    for (int k = 0; k < kRedWidth; ++k) mx[k] = 0.0;
+    for_rows_A(P, W.Aval, W.x, [&](int i, double ax) {
+      const double einv = 1.0 / W.E[i];
+      const double zi = W.z[i];
+      const double rp = ax - zi;
+      mx[0] = fmax(mx[0], fabs(einv * rp));
+      mx[1] = fmax(mx[1], fabs(einv * ax));
+      mx[2] = fmax(mx[2], fabs(einv * zi));
+      mx[3] = fmax(mx[3], fabs(rp));
+      mx[4] = fmax(mx[4], fabs(ax));
+      mx[5] = fmax(mx[5], fabs(zi));
+    });
+    for (int j = tid; j < n; j += T) {
+      const double dinv = 1.0 / W.D[j];
+      const double px = col_dot_P(P, W.Pval, W.x, j);
+      const double aty = col_dot_A(P, W.Aval, W.y, j);
+      const double rd = W.q[j] + px + aty;
+      mx[6] = fmax(mx[6], fabs(dinv * rd));
+      mx[7] = fmax(mx[7], fabs(dinv * W.q[j]));
+      mx[8] = fmax(mx[8], fabs(dinv * px));
+      mx[9] = fmax(mx[9], fabs(dinv * aty));
+      mx[10] = fmax(mx[10], fabs(rd));
+      mx[11] = fmax(mx[11], fabs(W.q[j]));
+      mx[12] = fmax(mx[12], fabs(px));
+      mx[13] = fmax(mx[13], fabs(aty));
+    }
+    block_reduce<kRedWidth, true>(mx, R);
+    prim_res = mx[0];
+    dual_res = cinv * mx[6];
+
+    if (can_check || last_iter) {
+      // ---- check_termination ---------------------------------------------------------------
+      const double eps_prim = S.eps_abs + S.eps_rel * fmax(mx[2], mx[1]);
+      const double eps_dual = S.eps_abs + S.eps_rel * cinv * fmax(mx[7], fmax(mx[9], mx[8]));
+      const bool prim_ok = prim_res < eps_prim, dual_ok = dual_res < eps_dual;
+      bool prim_inf = false, dual_inf = false;
+      if (!prim_ok) {
+        // is_primal_infeasible: dy projected on the polar of the recession cone of [l, u]
+        double a2[1] = {0.0};
+        for (int i = tid; i < m; i += T) {
+          double dy = W.dy[i];
+          if (W.u[i] > kInfty * kMinScaling) {
+            if (W.l[i] < -kInfty * kMinScaling) dy = 0.0; else dy = fmin(dy, 0.0);
+          } else if (W.l[i] < -kInfty * kMinScaling) {
+            dy = fmax(dy, 0.0);
+          }
+          W.dy[i] = dy;
+          a2[0] = fmax(a2[0], fabs(W.E[i] * dy));
+        }
+        block_reduce<1, true>(a2, R);
+        const double norm_dy = a2[0];
+        if (norm_dy > kDivisionTol) {
+          double lhs[1] = {0.0};
+          for (int i = tid; i < m; i += T) lhs[0] += W.u[i] * fmax(W.dy[i], 0.0) + W.l[i] * fmin(W.dy[i], 0.0);
+          block_reduce<1, false>(lhs, R);
+          if (lhs[0] < -S.eps_prim_inf * norm_dy) {
+            double na[1] = {0.0};
+            for (int j = tid; j < n; j += T) na[0] = fmax(na[0], fabs(col_dot_A(P, W.Aval, W.dy, j) / W.D[j]));
+            block_reduce<1, true>(na, R);
+            prim_inf = na[0] < S.eps_prim_inf * norm_dy;
+          }
+        }
+      }
+      if (!dual_ok) {
+        // is_dual_infeasible
+        double a2[1] = {0.0};
+        for (int j = tid; j < n; j += T) a2[0] = fmax(a2[0], fabs(W.D[j] * W.dx[j]));
+        block_reduce<1, true>(a2, R);
+        const double norm_dx = a2[0];
+        if (norm_dx > kDivisionTol) {
+          double qdx[1] = {0.0};
+          for (int j = tid; j < n; j += T) qdx[0] += W.q[j] * W.dx[j];
+          block_reduce<1, false>(qdx, R);
+          if (qdx[0] < -c * S.eps_dual_inf * norm_dx) {
+            double np_[1] = {0.0};
+            for (int j = tid; j < n; j += T) np_[0] = fmax(np_[0], fabs(col_dot_P(P, W.Pval, W.dx, j) / W.D[j]));
+            block_reduce<1, true>(np_, R);
+            if (np_[0] < c * S.eps_dual_inf * norm_dx) {
+              double viol[1] = {0.0};
+              for_rows_A(P, W.Aval, W.dx, [&](int i, double adx) {
+                const double a = adx / W.E[i];
+                if ((W.u[i] < kInfty * kMinScaling && a > S.eps_dual_inf * norm_dx) ||
+                    (W.l[i] > -kInfty * kMinScaling && a < -S.eps_dual_inf * norm_dx)) viol[0] = 1.0;
+              });
+              block_reduce<1, true>(viol, R);
+              dual_inf = viol[0] == 0.0;
+            }
+          }
+        }
+      }
+      int st = -1;
+      if (prim_ok && dual_ok) st = OCP_B200_QP_SOLVED;
+      else if (prim_inf) st = OCP_B200_QP_PRIMAL_INFEASIBLE;
+      else if (dual_inf) st = OCP_B200_QP_DUAL_INFEASIBLE;
+      if (A.trace && inst == 0 && can_check && n_trace < A.max_trace) {
+        if (tid == 0) {
+          double* tr = A.trace + size_t(n_trace) * OCP_B200_TRACE_WIDTH;
+          tr[0] = iter; tr[1] = prim_res; tr[2] = dual_res; tr[3] = rho; tr[4] = solves;
+          tr[5] = st < 0 ? OCP_B200_QP_UNSOLVED : st;
+        }
+        ++n_trace;
+      }
+      if (st >= 0) { status = st; done = true; clk.lap(OCP_B200_PHASE_CHECK); continue; }
+      if (last_iter) {
+        // approximate termination test with 10x tolerances, then MAX_ITER_REACHED
+        const double ep = 10.0 * S.eps_abs + 10.0 * S.eps_rel * fmax(mx[2], mx[1]);
+        const double ed = 10.0 * S.eps_abs + 10.0 * S.eps_rel * cinv * fmax(mx[7], fmax(mx[9], mx[8]));
+        status = (prim_res < ep && dual_res < ed) ? OCP_B200_QP_SOLVED_INACCURATE : OCP_B200_QP_MAX_ITER_REACHED;
+        done = true;
+        continue;
+      }
+    }
+
+    if (rho_time) {
+      // ---- adapt_rho: estimate from SCALED residuals, applied when it moved by > tolerance
+      const double pr = mx[3] / (fmax(mx[5], mx[4]) + 1e-10);
+      const double dr = mx[10] / (fmax(mx[11], fmax(mx[13], mx[12])) + 1e-10);
+      double est = rho * sqrt(pr / (dr + 1e-10));
+      est = fmin(fmax(est, kRhoMin), kRhoMax);
+      if (est > rho * S.adaptive_rho_tolerance || est < rho / S.adaptive_rho_tolerance) {
+        rho = est;
+        ++rho_updates;
+        rv = Rho(rho);
+        tri_assemble(P, W, rv, sigma);
+        factor_dispatch(P, W);
+      }
+    }
+    clk.lap(OCP_B200_PHASE_CHECK);
+  }
+  if (!done) { status = OCP_B200_QP_MAX_ITER_REACHED; }
+  if (A.trace && inst == 0 && tid == 0 && A.n_trace) *A.n_trace = n_trace;
+  const int iters_done = done ? iter - 1 : S.admm_max_iter;
+  out = QpResult{status, iters_done, solves, rho_updates, checks, prim_res, dual_res, rho};
+
+  // ---- store_solution: unscale in place (x <- D x, y <- E y / c), or NaN for a certificate
+  const bool has_sol = status != OCP_B200_QP_PRIMAL_INFEASIBLE && status != OCP_B200_QP_DUAL_INFEASIBLE;
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  for (int j = tid; j < n; j += T) W.x[j] = has_sol ? W.D[j] * W.x[j] : nanv;
+  for (int i = tid; i < m; i += T) W.y[i] = has_sol ? cinv * W.E[i] * W.y[i] : nanv;
+  __syncthreads();
+}
+
+// persistent kernel: CTAs pull instances from A.counter
+template <bool kAllSmem>
+__global__ void __launch_bounds__(kDirectThreads, 1)
+admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArgs A, const uint32_t smem_mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red_buf[2 * (kDirectThreads / 32) * kRedWidth];
+  __shared__ int s_inst;
+  Work W;
+  carve<kAllSmem>(W, P, smem_mask, reinterpret_cast<double*>(smem_raw),
+                  kAllSmem ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles);
+  PatternDev PL = P;
+  if (kAllSmem || (smem_mask >> AR_IDX & 1u)) {
+    // index structures move into shared memory once per CTA (same offsets as the global arena)
+    for (int k = threadIdx.x; k < P.idx_entries; k += blockDim.x) W.idx[k] = P.idx_base[k];
+    auto move = [&](const idx_t*& ptr) { ptr = W.idx + (ptr - P.idx_base); };
+    move(PL.a_colptr); move(PL.a_rowidx); move(PL.a_rowptr); move(PL.a_colidx); move(PL.a_perm);
+    move(PL.p_colptr); move(PL.p_rowidx); move(PL.rows_long); move(PL.rows_short);
+    __syncthreads();
+  }
+  Reducer R{red_buf, 0, (kDirectThreads / 32) * kRedWidth};
+  while (true) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= A.B) break;
+    QpResult res;
+    solve_instance(PL, S, A, W, R, inst, res);
+    write_outputs(P, A, W.x, W.y, R, inst, res);
+  }
+}
+
+}  // namespace direct
+}  // namespace ocpb200

@@ -23,61 +23,10 @@
 // rebuilds are decided on the device.
 #pragma once
 
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "ocp_b200.h"
+#include "admm_common.cuh"
 
 namespace ocpb200 {
-
-constexpr double kInfty = 1e30, kMinScaling = 1e-4, kMaxScaling = 1e4;
-constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoTol = 1e-4, kRhoEqOverIneq = 1e3;
-constexpr double kDivisionTol = 1e-30;
-constexpr int kRedWidth = 16;          // max values per block reduction
-constexpr int kMaxWarps = 32;
-
-typedef uint16_t idx_t;
-
-// Index structures of one sparsity pattern (device pointers, shared by every instance)
-struct PatternDev {
-  int n, m, nnz_a, nnz_p, nnz_h;
-  int nblk, minv_doubles, max_bs;
-  int n_long, n_short;
-  const idx_t* a_colptr;   // n+1
-  const idx_t* a_rowidx;   // nnz_a
-  const idx_t* a_rowptr;   // m+1
-  const idx_t* a_colidx;   // nnz_a, CSR order
-  const idx_t* a_perm;     // nnz_a, CSR position -> CSC position
-  const idx_t* p_colptr;   // n+1   (symmetrised full pattern of the upper triangle of H)
-  const idx_t* p_rowidx;   // nnz_p
-  const int* p_src;        // nnz_p, index into the caller's H values (upper-triangle twin)
-  const idx_t* blk_ptr;    // nblk+1
-  const idx_t* blk_of_col; // n
-  const int* minv_off;     // nblk
-  const idx_t* rows_long;  // rows handled by 4 lanes each
-  const idx_t* rows_short; // rows handled by one thread each
-};
-
-struct SolveArgs {
-  int B;
-  // QP data, one row per instance
-  const double* h_vals; int ld_h;
-  const double* q; int ld_n;
-  const double* a_vals; int ld_a;
-  const double* l; const double* u; int ld_m;
-  // outputs
-  double* sol_x;      // B*n   unscaled primal solution (may be null)
-  double* sol_y;      // B*m   unscaled dual solution (may be null)
-  double* info;       // B*OCP_B200_NINFO (may be null)
-  // SQP update: x_iter[b*N + i] += alpha * sol[np + i]; stats accumulated (may be null)
-  double* x_iter; int np; int N; double sqp_alpha;
-  double* stats; int first_step;
-  // trace of instance 0 (may be null)
-  double* trace; int max_trace; int* n_trace;
-  // scheduling + streaming workspace
-  int* counter;
-  double* slab; size_t slab_doubles;
-};
+namespace pcg {
 
 // Where the per-instance state lives (shared memory or a global slab)
 struct Work {
@@ -102,95 +51,6 @@ __device__ inline void carve(Work& W, double* base, const PatternDev& P) {
   for (int k = 0; k < 10; ++k) { *mv[k] = p; p += P.m; }
   W.Minv = p; p += P.minv_doubles;
   W.ctype = reinterpret_cast<signed char*>(p);
-}
-
-// ---------------------------------------------------------------------------------------
-// block reductions: warp shuffles, then one shared-memory exchange; every thread returns
-// with the same result.  Two alternating exchange buffers make one barrier per call enough.
-// ---------------------------------------------------------------------------------------
-struct Reducer {
-  double* buf;   // 2 * kMaxWarps * kRedWidth doubles of shared memory
-  int parity;
-};
-
-template <int NV, bool kMax>
-__device__ __forceinline__ void block_reduce(double (&v)[NV], Reducer& R) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double a = v[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double b = __shfl_xor_sync(0xffffffffu, a, o);
-      a = kMax ? fmax(a, b) : a + b;
-    }
-    v[k] = a;
-  }
-  double* buf = R.buf + R.parity * (kMaxWarps * kRedWidth);
-  R.parity ^= 1;
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) buf[warp * NV + k] = v[k];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double a = buf[k];
-    for (int w = 1; w < nw; ++w) a = kMax ? fmax(a, buf[w * NV + k]) : a + buf[w * NV + k];
-    v[k] = a;
-  }
-}
-
-__device__ __forceinline__ double limit_scaling(double v) {
-  v = v < kMinScaling ? 1.0 : v;
-  return v > kMaxScaling ? kMaxScaling : v;
-}
-
-// ---------------------------------------------------------------------------------------
-// sparse kernels over one instance.  A rows go through the CSR view (values fetched
-// through the CSR->CSC permutation), A and P columns through the CSC arrays.
-// ---------------------------------------------------------------------------------------
-template <typename F>
-__device__ __forceinline__ void for_rows_A(const PatternDev& P, const double* __restrict__ Aval,
-                                           const double* __restrict__ src, F f) {
-  const int tid = threadIdx.x, T = blockDim.x;
-  // long rows: 4 lanes per row
-  for (int base = 0; base < P.n_long; base += (T >> 2)) {
-    const int idx = base + (tid >> 2);
-    const bool valid = idx < P.n_long;
-    double s = 0.0;
-    int row = 0;
-    if (valid) {
-      row = P.rows_long[idx];
-      const int e = P.a_rowptr[row + 1];
-      for (int k = P.a_rowptr[row] + (tid & 3); k < e; k += 4) s += Aval[P.a_perm[k]] * src[P.a_colidx[k]];
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (valid && (tid & 3) == 0) f(row, s);
-  }
-  for (int idx = tid; idx < P.n_short; idx += T) {
-    const int row = P.rows_short[idx];
-    double s = 0.0;
-    const int e = P.a_rowptr[row + 1];
-    for (int k = P.a_rowptr[row]; k < e; ++k) s += Aval[P.a_perm[k]] * src[P.a_colidx[k]];
-    f(row, s);
-  }
-}
-
-__device__ __forceinline__ double col_dot_A(const PatternDev& P, const double* __restrict__ Aval,
-                                            const double* __restrict__ v, int j) {
-  double s = 0.0;
-  const int e = P.a_colptr[j + 1];
-  for (int k = P.a_colptr[j]; k < e; ++k) s += Aval[k] * v[P.a_rowidx[k]];
-  return s;
-}
-__device__ __forceinline__ double col_dot_P(const PatternDev& P, const double* __restrict__ Pval,
-                                            const double* __restrict__ v, int j) {
-  double s = 0.0;
-  const int e = P.p_colptr[j + 1];
-  for (int k = P.p_colptr[j]; k < e; ++k) s += Pval[k] * v[P.p_rowidx[k]];
-  return s;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -280,11 +140,6 @@ __device__ __forceinline__ double apply_preconditioner(const PatternDev& P, cons
 // ---------------------------------------------------------------------------------------
 // one QP, solved by the whole CTA
 // ---------------------------------------------------------------------------------------
-struct QpResult {
-  int status, iters, pcg_iters, rho_updates, checks;
-  double prim_res, dual_res, rho;
-};
-
 __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settings& S, const SolveArgs& A,
                                       const Work& W, Reducer& R, int inst, QpResult& out) {
   const int tid = threadIdx.x, T = blockDim.x;
@@ -634,7 +489,7 @@ admm_solve_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArgs
   } else {
     carve(W, A.slab + size_t(blockIdx.x) * A.slab_doubles, P);
   }
-  Reducer R{red_buf, 0};
+  Reducer R{red_buf, 0, kMaxWarps * kRedWidth};
   while (true) {
     if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
     __syncthreads();
@@ -643,54 +498,9 @@ admm_solve_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArgs
     if (inst >= A.B) break;
     QpResult res;
     solve_instance(PL, S, A, W, R, inst, res);
-    const bool solved_setup = res.status != OCP_B200_QP_UNSOLVED || res.iters > 0;
-    // outputs
-    if (A.sol_x)
-      for (int j = threadIdx.x; j < P.n; j += blockDim.x) A.sol_x[size_t(inst) * P.n + j] = solved_setup ? W.x[j] : 0.0;
-    if (A.sol_y)
-      for (int i = threadIdx.x; i < P.m; i += blockDim.x) A.sol_y[size_t(inst) * P.m + i] = solved_setup ? W.y[i] : 0.0;
-    double nrm[1] = {0.0};
-    if (A.x_iter) {
-      double* xi = A.x_iter + size_t(inst) * A.N;
-      for (int i = threadIdx.x; i < A.N; i += blockDim.x) {
-        const double dx = solved_setup ? A.sqp_alpha * W.x[A.np + i] : 0.0;
-        xi[i] += dx;
-        nrm[0] += dx * dx;
-      }
-      block_reduce<1, false>(nrm, R);
-    }
-    if (threadIdx.x == 0) {
-      if (A.info) {
-        double* f = A.info + size_t(inst) * OCP_B200_NINFO;
-        f[OCP_B200_INFO_STATUS] = res.status; f[OCP_B200_INFO_ITERS] = res.iters;
-        f[OCP_B200_INFO_PCG_ITERS] = res.pcg_iters; f[OCP_B200_INFO_PRIM_RES] = res.prim_res;
-        f[OCP_B200_INFO_DUAL_RES] = res.dual_res; f[OCP_B200_INFO_RHO] = res.rho;
-        f[OCP_B200_INFO_RHO_UPDATES] = res.rho_updates; f[OCP_B200_INFO_CHECKS] = res.checks;
-      }
-      if (A.stats) {
-        double* s = A.stats + size_t(inst) * OCP_B200_NSTATS;
-        if (A.first_step) for (int k = 0; k < OCP_B200_NSTATS; ++k) s[k] = 0.0;
-        s[OCP_B200_STAT_QP_STATUS] = res.status;
-        s[OCP_B200_STAT_SQP_STEPS] += 1.0;
-        s[OCP_B200_STAT_ADMM_ITERS] += res.iters;
-        s[OCP_B200_STAT_PCG_ITERS] += res.pcg_iters;
-        s[OCP_B200_STAT_PRIM_RES] = res.prim_res;
-        s[OCP_B200_STAT_DUAL_RES] = res.dual_res;
-        s[OCP_B200_STAT_RHO_UPDATES] += res.rho_updates;
-        s[OCP_B200_STAT_LAST_ADMM] = res.iters;
-        s[OCP_B200_STAT_LAST_RHO] = res.rho;
-        s[OCP_B200_STAT_CHECKS] += res.checks;
-        s[OCP_B200_STAT_STEP_NORM] = sqrt(nrm[0]);
-      }
-    }
-    __syncthreads();
+    write_outputs(P, A, W.x, W.y, R, inst, res);
   }
 }
 
-// f -> stats column, after the objective kernel of the stage library has run
-__global__ void store_objective_kernel(int B, const double* __restrict__ f, double* __restrict__ stats) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) stats[size_t(b) * OCP_B200_NSTATS + OCP_B200_STAT_OBJECTIVE] = f[b];
-}
-
+}  // namespace pcg
 }  // namespace ocpb200

@@ -16,8 +16,18 @@
 #include <string>
 #include <vector>
 
-#include "admm_kernel.cuh"
+#include "admm_pcg_kernel.cuh"
+#include "direct_launch.h"
 #include "ocp_b200_model.h"
+
+namespace ocpb200 {
+// f -> stats column, after the objective kernel of the stage library has run
+__global__ void store_objective_kernel(int B, const double* __restrict__ f, double* __restrict__ stats) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) stats[size_t(b) * OCP_B200_NSTATS + OCP_B200_STAT_OBJECTIVE] = f[b];
+}
+
+}  // namespace ocpb200
 
 namespace {
 
@@ -83,10 +93,13 @@ struct ocp_b200_solver {
   // launch configuration
   int num_sms = 0, threads = 512, resident = 0, smem_bytes = 0, max_ctas = 0;
   size_t slab_doubles = 0;
+  int use_direct = 0;          // 1: admm_direct_kernel (block-tridiagonal LDL'), 0: PCG kernel
+  uint32_t smem_mask = 0;      // direct kernel: which state arrays live in shared memory
   // workspaces (device)
   DevBuf<double> hv, q, av, l, u, solx, soly, info, slab, trace;
   DevBuf<double> x, p, frames, lbx, ubx, lbg, ubg, f, stats;
   DevBuf<int> counter;
+  DevBuf<long long> phase;
   cudaStream_t stream = nullptr;
   long long launches = 0;
   // optional per-kernel timing (ocp_b200_set_profiling): event pairs around every launch
@@ -176,8 +189,9 @@ int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
     return off;
   };
   const size_t o_acp = push(ac), o_ari = push(ar), o_arp = push(rowptr), o_aci = push(colidx), o_perm = push(perm),
-               o_pcp = push(pc), o_pri = push(pr), o_blk = push(blk), o_bof = push(blk_of), o_rl = push(rows_long),
-               o_rs = push(rows_short);
+               o_pcp = push(pc), o_pri = push(pr), o_rl = push(rows_long), o_rs = push(rows_short);
+  const size_t direct_entries = arena.size();   // what the direct kernel stages in shared memory
+  const size_t o_blk = push(blk), o_bof = push(blk_of);   // PCG kernel only
   CUDA_TRY(s->d_idx.reserve(arena.size()));
   CUDA_TRY(cudaMemcpy(s->d_idx.p, arena.data(), arena.size() * sizeof(idx_t), cudaMemcpyHostToDevice));
   std::vector<int> iarena(psrc);
@@ -196,27 +210,93 @@ int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
   P.blk_of_col = base + o_bof; P.rows_long = base + o_rl; P.rows_short = base + o_rs;
   P.p_src = s->d_int.p; P.minv_off = s->d_int.p + o_minv;
 
-  // shared-memory budget of the resident variant: state + staged index arrays
-  const size_t idx_entries = size_t(pad8(n + 1)) * 2 + size_t(pad8(s->nnz_a)) * 3 + pad8(m + 1) + pad8(s->nnz_p) +
-                             pad8(nblk + 1) + pad8(n) + pad8(P.n_long) + pad8(P.n_short);
-  const size_t want = ocpb200::work_doubles(P) * sizeof(double) + idx_entries * sizeof(idx_t);
+  P.idx_entries = static_cast<int>(direct_entries);
+  P.idx_base = base;
+
+  // bordered block-tridiagonal structure of K for the direct kernel: border = the np parameter
+  // columns, blocks = groups of G consecutive stages (G the largest divisor of the horizon that
+  // keeps a block at <= 20 columns, so that long horizons of small stages take fewer
+  // sequential block steps)
+  {
+    int G = 1;
+    for (int g = 1; g <= s->horizon; ++g)
+      if (s->horizon % g == 0 && g * s->nf <= 20) G = g;
+    const int bs = G * s->nf, nb = s->horizon / G;
+    P.tri_np = s->np; P.tri_bs = bs; P.tri_nb = nb; P.tri_ld = (bs + 2) & ~1;   // even pitch: 16-byte aligned block rows
+    bool ok = bs <= 64 && s->np <= 64;
+    auto blk_of_col = [&](int j) { return j < s->np ? -1 : (j - s->np) / bs; };
+    for (int j = 0; j < n && ok; ++j)
+      for (int k = pc[j]; k < pc[j + 1]; ++k) {
+        const int bi = blk_of_col(pr[k]), bj = blk_of_col(j);
+        if (bi >= 0 && bj >= 0 && std::abs(bi - bj) > 1) { ok = false; break; }
+      }
+    for (int i = 0; i < m && ok; ++i) {
+      int lo = 1 << 30, hi = -1;
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int bj = blk_of_col(colidx[k]);
+        if (bj >= 0) { lo = std::min(lo, bj); hi = std::max(hi, bj); }
+      }
+      if (hi >= 0 && hi - lo > 1) ok = false;
+    }
+    P.tri_ok = ok ? 1 : 0;
+  }
+  return OCP_B200_OK;
+}
+
+// Chooses the kernel for the current settings and lays out its per-instance state: shared
+// memory first, in the priority order of direct::ArrayId, the rest in a per-CTA global slab.
+int plan_launch(ocp_b200_solver* s) {
+  const PatternDev& P = s->pat;
   int max_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-  cudaFuncAttributes fa{};
-  CUDA_TRY(cudaFuncGetAttributes(&fa, ocpb200::admm_solve_kernel<true>));
-  const size_t avail = size_t(max_optin) - fa.sharedSizeBytes;
-  s->resident = want <= avail ? 1 : 0;
-  s->smem_bytes = s->resident ? static_cast<int>(want) : 0;
-  if (s->resident)
-    CUDA_TRY(cudaFuncSetAttribute(ocpb200::admm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  s->smem_bytes));
-  s->slab_doubles = (ocpb200::work_doubles(P) + 15) & ~size_t(15);
+  s->use_direct = (s->settings.pcg_precond == OCP_B200_PRECOND_BLOCK_TRIDIAG && P.tri_ok) ? 1 : 0;
   int per_sm = 1;
-  if (s->resident)
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ocpb200::admm_solve_kernel<true>, s->threads,
-                                                           s->smem_bytes));
-  else
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ocpb200::admm_solve_kernel<false>, s->threads, 0));
+  if (s->use_direct) {
+    namespace D = ocpb200::direct;
+    s->threads = D::block_threads();
+    D::KernelInfo ki{};
+    CUDA_TRY(D::kernel_info(true, &ki));
+    D::KernelInfo ki2{};
+    CUDA_TRY(D::kernel_info(false, &ki2));
+    const int stat = std::max(ki.static_smem, ki2.static_smem);
+    size_t avail = (size_t(max_optin) - stat) / sizeof(double), used = 0, slab = 0;
+    uint32_t mask = 0;
+    const int count = D::plan_array_count();
+    for (int id = 0; id < count; ++id) {
+      const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
+      if (used + sz <= avail) { mask |= 1u << id; used += sz; }
+      else slab += sz;
+    }
+    s->smem_mask = mask;
+    s->smem_bytes = static_cast<int>(used * sizeof(double));
+    s->resident = mask == (1u << count) - 1u ? 1 : 0;
+    s->slab_doubles = (slab + 15) & ~size_t(15);
+    // the attribute is per function, not per handle: always opt in to the maximum so that handles
+    // of different problems can coexist in one process
+    CUDA_TRY(D::set_max_dynamic_smem(true, max_optin - stat));
+    CUDA_TRY(D::set_max_dynamic_smem(false, max_optin - stat));
+    CUDA_TRY(D::occupancy(s->resident != 0, s->threads, s->smem_bytes, &per_sm));
+  } else {
+    s->threads = 512;
+    const size_t idx_entries = size_t(pad8(P.n + 1)) * 2 + size_t(pad8(P.nnz_a)) * 3 + pad8(P.m + 1) + pad8(P.nnz_p) +
+                               pad8(P.nblk + 1) + pad8(P.n) + pad8(P.n_long) + pad8(P.n_short);
+    const size_t want = ocpb200::pcg::work_doubles(P) * sizeof(double) + idx_entries * sizeof(idx_t);
+    cudaFuncAttributes fa{};
+    CUDA_TRY(cudaFuncGetAttributes(&fa, ocpb200::pcg::admm_solve_kernel<true>));
+    const size_t avail = size_t(max_optin) - fa.sharedSizeBytes;
+    s->resident = want <= avail ? 1 : 0;
+    s->smem_bytes = s->resident ? static_cast<int>(want) : 0;
+    if (s->resident)
+      CUDA_TRY(cudaFuncSetAttribute(ocpb200::pcg::admm_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    max_optin - static_cast<int>(fa.sharedSizeBytes)));
+    s->slab_doubles = (ocpb200::pcg::work_doubles(P) + 15) & ~size_t(15);
+    if (s->resident)
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ocpb200::pcg::admm_solve_kernel<true>,
+                                                             s->threads, s->smem_bytes));
+    else
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ocpb200::pcg::admm_solve_kernel<false>,
+                                                             s->threads, 0));
+  }
   s->max_ctas = std::max(1, per_sm) * s->num_sms;
   return OCP_B200_OK;
 }
@@ -248,7 +328,7 @@ int check_settings(const ocp_b200_settings* t) {
   if (t->sqp_step_num < 0 || t->admm_max_iter < 1 || t->check_termination < 0 || t->scaling_iters < 0 ||
       t->pcg_max_iter < 1 || !(t->rho > 0) || !(t->sigma > 0) || !(t->relax > 0 && t->relax < 2) ||
       !(t->eps_abs >= 0) || !(t->eps_rel >= 0) || !(t->pcg_tol > 0) || t->pcg_precond < 0 ||
-      t->pcg_precond > OCP_B200_PRECOND_BLOCK_JACOBI)
+      t->pcg_precond > OCP_B200_PRECOND_BLOCK_TRIDIAG)
     return fail(OCP_B200_ERR_INVALID, "settings out of range");
   return OCP_B200_OK;
 }
@@ -272,15 +352,28 @@ int launch_admm(ocp_b200_solver* s, SolveArgs& A, cudaStream_t st) {
   CUDA_TRY(s->counter.reserve(1));
   CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
   A.counter = s->counter.p;
+  A.phase = s->profiling ? s->phase.p : nullptr;
   const int grid = std::min(A.B, s->max_ctas);
   ProfScope prof(s, OCP_B200_PROF_ADMM, st);
-  if (s->resident) {
+  if (s->use_direct) {
+    A.slab = nullptr; A.slab_doubles = s->slab_doubles;
+    if (!s->resident) {
+      CUDA_TRY(s->slab.reserve(size_t(grid) * s->slab_doubles));
+      A.slab = s->slab.p;
+    }
+    CUDA_TRY(ocpb200::direct::launch(s->resident != 0, grid, s->threads, s->smem_bytes, st, s->pat, s->settings, A,
+                                     s->smem_mask));
+  } else if (s->resident) {
     A.slab = nullptr; A.slab_doubles = 0;
-    ocpb200::admm_solve_kernel<true><<<grid, s->threads, s->smem_bytes, st>>>(s->pat, s->settings, A);
+    ocp_b200_settings t = s->settings;
+    if (t.pcg_precond == OCP_B200_PRECOND_BLOCK_TRIDIAG) t.pcg_precond = OCP_B200_PRECOND_BLOCK_JACOBI;
+    ocpb200::pcg::admm_solve_kernel<true><<<grid, s->threads, s->smem_bytes, st>>>(s->pat, t, A);
   } else {
     CUDA_TRY(s->slab.reserve(size_t(grid) * s->slab_doubles));
     A.slab = s->slab.p; A.slab_doubles = s->slab_doubles;
-    ocpb200::admm_solve_kernel<false><<<grid, s->threads, 0, st>>>(s->pat, s->settings, A);
+    ocp_b200_settings t = s->settings;
+    if (t.pcg_precond == OCP_B200_PRECOND_BLOCK_TRIDIAG) t.pcg_precond = OCP_B200_PRECOND_BLOCK_JACOBI;
+    ocpb200::pcg::admm_solve_kernel<false><<<grid, s->threads, 0, st>>>(s->pat, t, A);
   }
   CUDA_TRY(cudaGetLastError());
   s->launches++;
@@ -347,7 +440,7 @@ void ocp_b200_default_settings(ocp_b200_settings* s) {
   s->rho = 0.1; s->sigma = 1e-6; s->relax = 1.6;
   s->scaling_iters = 10; s->check_termination = 25;
   s->adaptive_rho = 1; s->adaptive_rho_interval = 0; s->adaptive_rho_tolerance = 5.0;
-  s->pcg_max_iter = 500; s->pcg_tol = 1e-10; s->pcg_precond = OCP_B200_PRECOND_BLOCK_JACOBI;
+  s->pcg_max_iter = 500; s->pcg_tol = 1e-10; s->pcg_precond = OCP_B200_PRECOND_BLOCK_TRIDIAG;
 }
 
 int ocp_b200_abi_version(void) { return OCP_B200_ABI_VERSION; }
@@ -402,6 +495,8 @@ int ocp_b200_create(const ocp_b200_problem_desc* d, const ocp_b200_settings* set
     return bail(fail(OCP_B200_ERR_CUDA, "cudaStreamCreate failed"));
   int rc = upload_pattern(s, d->num_blocks, d->block_ptr);
   if (rc != OCP_B200_OK) return bail(rc);
+  rc = plan_launch(s);
+  if (rc != OCP_B200_OK) return bail(rc);
   if (d->model_library && d->model_library[0]) {
     rc = load_model(s, d->model_library);
     if (rc != OCP_B200_OK) return bail(rc);
@@ -419,6 +514,7 @@ int ocp_b200_destroy(ocp_b200_solver* s) {
                             &s->x, &s->p, &s->frames, &s->lbx, &s->ubx, &s->lbg, &s->ubg, &s->f, &s->stats};
   for (DevBuf<double>* b : bufs) b->release();
   s->counter.release();
+  s->phase.release();
   // the stage library stays loaded: its kernels are registered with the CUDA runtime and
   // unloading a module that another handle still uses would invalidate them
   delete s;
@@ -428,7 +524,12 @@ int ocp_b200_destroy(ocp_b200_solver* s) {
 int ocp_b200_update_settings(ocp_b200_solver* s, const ocp_b200_settings* settings) {
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
   RC_TRY(check_settings(settings));
+  const int old = s->settings.pcg_precond;
   s->settings = *settings;
+  if (old != settings->pcg_precond) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    RC_TRY(plan_launch(s));
+  }
   return OCP_B200_OK;
 }
 
@@ -587,6 +688,21 @@ long long ocp_b200_launch_count(const ocp_b200_solver* s) { return s ? s->launch
 int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled) {
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
   s->profiling = enabled ? 1 : 0;
+  if (enabled) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(s->phase.reserve(OCP_B200_NPHASE));
+    CUDA_TRY(cudaMemset(s->phase.p, 0, OCP_B200_NPHASE * sizeof(long long)));
+  }
+  return OCP_B200_OK;
+}
+
+int ocp_b200_get_phase_cycles(ocp_b200_solver* s, long long* cycles) {
+  if (!s || !cycles) return fail(OCP_B200_ERR_INVALID, "solver/cycles is NULL");
+  if (!s->phase.p) { for (int k = 0; k < OCP_B200_NPHASE; ++k) cycles[k] = 0; return OCP_B200_OK; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(cycles, s->phase.p, OCP_B200_NPHASE * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(s->phase.p, 0, OCP_B200_NPHASE * sizeof(long long)));
   return OCP_B200_OK;
 }
 
@@ -619,7 +735,7 @@ int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int*
   if (nnz_h) *nnz_h = s->nnz_h;
   if (nnz_a) *nnz_a = s->nnz_a;
   if (smem_bytes) *smem_bytes = s->smem_bytes;
-  if (resident) *resident = s->resident;
+  if (resident) *resident = s->resident | (s->use_direct << 1);
   return OCP_B200_OK;
 }
 

@@ -117,8 +117,8 @@ def test_admm_trace_matches_oracle(problems, native):
     assert rel_err(x, ox) < REL_SOLUTION
 
 
-@pytest.mark.parametrize("precond", [0, 1])
-def test_preconditioners_agree(problems, native, precond):
+@pytest.mark.parametrize("precond", [0, 1, 2])
+def test_linear_system_solvers_agree(problems, native, precond):
     prob, ora = problems("quadrotor")
     hv, q, av, l, u = _qp_case(prob, ora, 9, B=2)
     s = prob.get_settings()
@@ -143,17 +143,39 @@ def test_sqp_solve_matches_oracle(problems, native, name, B, alpha, steps):
     s = prob.get_settings()
     s.sqp_alpha, s.sqp_step_num = alpha, steps
     prob.solver.update_settings(s)
-    x = np.zeros((B, prob.N)); f = np.zeros(B); st = np.zeros((B, native.NSTATS))
+    # start every instance from its initial state held over the horizon (x = 0 makes the first
+    # cart-pole QP primal infeasible, which is covered by test_infeasible_step_propagates_nan)
+    x0 = np.tile(frames, (1, prob.horizon))
+    x = x0.copy(); f = np.zeros(B); st = np.zeros((B, native.NSTATS))
     prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, f, st)
     ora.set_schedule(steps, alpha)
     ora.set_qp_settings(_oracle.settings_from_b200(s))
-    ox, of, ost = ora.solve_batch(frames, refs)
+    ox, of, ost = ora.solve_batch(frames, refs, x0=x0)
+    assert np.isfinite(ox).all()
     assert np.array_equal(st[:, native.STAT["sqp_steps"]], ost[:, 1])
     assert np.array_equal(st[:, native.STAT["admm_iters"]], ost[:, 2])
     assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
     assert rel_err(x, ox) < REL_SOLUTION
     assert np.allclose(f, of, rtol=1e-6, atol=1e-9)
     assert np.allclose(st[:, native.STAT["objective"]], of, rtol=1e-6, atol=1e-9)
+
+
+def test_infeasible_step_propagates_nan(problems, native):
+    """Cart-pole from x = 0 with the pole pinned near theta = pi: the first QP is primal infeasible;
+    OSQP returns NaN and the reference adds it to the iterate unchecked (SQPOptimizationSolver.cpp:
+    155-177).  Both sides must agree on that, status included."""
+    prob, ora = problems("cartpole")
+    frames, refs = prob.sample_inputs(2, 0xB200 + 2)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = 0.5, 2
+    prob.solver.update_settings(s)
+    x = np.zeros((2, prob.N)); st = np.zeros((2, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, None, st)
+    ora.set_schedule(2, 0.5)
+    ora.set_qp_settings(_oracle.settings_from_b200(s))
+    ox, of, ost = ora.solve_batch(frames, refs)
+    assert np.array_equal(np.isnan(x), np.isnan(ox))
+    assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
 
 
 def test_batch_equals_single_instance(problems, native):
