@@ -175,6 +175,7 @@ def b200_arm(args):
     import torch.distributed as dist
 
     import optimal_control_problem_b200 as ocp
+    from optimal_control_problem_b200.sharding import gather_shards
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,8 +204,7 @@ def b200_arm(args):
     d_lbg = torch.from_numpy(prob.lbg).to(dev); d_ubg = torch.from_numpy(prob.ubg).to(dev)
     d_x = torch.zeros(B, prob.N, **f64); d_f = torch.zeros(B, **f64); d_stats = torch.zeros(B, ocp.NSTATS, **f64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    if world > 1:
-        g_x = torch.empty(world * B, prob.N, **f64); g_stats = torch.empty(world * B, ocp.NSTATS, **f64)
+    gathered = {}
     stream = torch.cuda.current_stream()
 
     def device_step():
@@ -213,8 +213,8 @@ def b200_arm(args):
                                d_lbg.data_ptr(), d_ubg.data_ptr(), d_x.data_ptr(), d_f.data_ptr(), d_stats.data_ptr(),
                                stream.cuda_stream)
         if world > 1:  # the one collective of the path: gather solutions and statistics
-            dist.all_gather_into_tensor(g_x, d_x)
-            dist.all_gather_into_tensor(g_stats, d_stats)
+            gathered["x"] = gather_shards(d_x, world * B)
+            gathered["stats"] = gather_shards(d_stats, world * B)
 
     def barrier():
         if world > 1:

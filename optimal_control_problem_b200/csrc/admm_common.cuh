@@ -127,6 +127,7 @@ __device__ __forceinline__ void for_rows_A(const PatternDev& P, const double* __
     if (valid) {
       row = P.rows_long[idx];
       const int e = P.a_rowptr[row + 1];
+#pragma unroll 4
       for (int k = P.a_rowptr[row] + (tid & 3); k < e; k += 4) s += Aval[P.a_perm[k]] * src[P.a_colidx[k]];
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -137,6 +138,7 @@ __device__ __forceinline__ void for_rows_A(const PatternDev& P, const double* __
     const int row = P.rows_short[idx];
     double s = 0.0;
     const int e = P.a_rowptr[row + 1];
+#pragma unroll 4
     for (int k = P.a_rowptr[row]; k < e; ++k) s += Aval[P.a_perm[k]] * src[P.a_colidx[k]];
     f(row, s);
   }
@@ -146,6 +148,7 @@ __device__ __forceinline__ double col_dot_A(const PatternDev& P, const double* _
                                             const double* __restrict__ v, int j) {
   double s = 0.0;
   const int e = P.a_colptr[j + 1];
+#pragma unroll 4
   for (int k = P.a_colptr[j]; k < e; ++k) s += Aval[k] * v[P.a_rowidx[k]];
   return s;
 }
@@ -153,6 +156,7 @@ __device__ __forceinline__ double col_dot_P(const PatternDev& P, const double* _
                                             const double* __restrict__ v, int j) {
   double s = 0.0;
   const int e = P.p_colptr[j + 1];
+#pragma unroll 4
   for (int k = P.p_colptr[j]; k < e; ++k) s += Pval[k] * v[P.p_rowidx[k]];
   return s;
 }

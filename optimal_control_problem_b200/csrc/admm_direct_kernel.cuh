@@ -35,13 +35,20 @@
 namespace ocpb200 {
 namespace direct {
 
-constexpr int kDirectThreads = 256;   // 255 registers per thread: the unrolled block code does not spill
+// Placement of the per-instance state:
+//   PLACE_MIXED  run-time mask (host plan: shared memory first, in ArrayId order; rest in a global slab)
+//   PLACE_SMEM   everything in shared memory, one CTA per SM (pointers are shared-space: LDS/STS)
+//   PLACE_MULTI  vectors, A values and small scratch in shared memory, factor blocks / index
+//                arrays / rarely used vectors in global memory (L2-resident): ~65 KB per CTA, so that
+//                three CTAs share an SM and hide each other's dependent-latency chains
+enum Placement { PLACE_MIXED = 0, PLACE_SMEM = 1, PLACE_MULTI = 2 };
 
 // arrays of the per-instance state, in shared-memory priority order
 enum ArrayId {
-  AR_X = 0, AR_Q, AR_B, AR_Z, AR_Y, AR_L, AR_U, AR_CTYPE, AR_AVAL, AR_DINV, AR_LSUB, AR_IDX, AR_PVAL, AR_BORDER,
-  AR_D, AR_E, AR_DX, AR_DY, AR_COUNT
+  AR_X = 0, AR_Q, AR_B, AR_Z, AR_Y, AR_L, AR_U, AR_CTYPE, AR_W, AR_AVAL, AR_SCRATCH, AR_IDX, AR_DINV, AR_LSUB, AR_PVAL,
+  AR_LP, AR_D, AR_E, AR_DX, AR_DY, AR_COUNT
 };
+__host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX; }
 
 struct Work {
   double *x, *q, *b, *z, *y, *l, *u;
@@ -49,7 +56,10 @@ struct Work {
   double *Aval, *Dinv, *Lsub;
   idx_t* idx;
   double *Pval;
-  double *Lp, *Dp, *S, *Sp, *xp, *piv;   // border: L_pk [np x N], D_p^-1 [np x (np+1)], scratch blocks
+  double *Lp, *Dp, *Dp2, *S, *Sp, *xp, *piv;   // border: L_pk [np x N], D_p^-1 [np x (np+1)], scratch (two sets)
+  int s_stride, sp_stride;
+  long long* phase;   // cycle counters of CTA 0 (null unless profiling)
+  double *w;                        // rho .* z - y, kept current by the update phase
   double *D, *E, *dx, *dy;
 };
 
@@ -57,14 +67,15 @@ __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
   const size_t n = P.n, m = P.m, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb, np = P.tri_np;
   switch (id) {
     case AR_X: case AR_Q: case AR_B: case AR_D: case AR_DX: return (n + 1) & ~size_t(1);
-    case AR_Z: case AR_Y: case AR_L: case AR_U: case AR_E: case AR_DY: return (m + 1) & ~size_t(1);
+    case AR_Z: case AR_Y: case AR_L: case AR_U: case AR_E: case AR_DY: case AR_W: return (m + 1) & ~size_t(1);
     case AR_CTYPE: return (m + 7) / 8;
     case AR_AVAL: return (size_t(P.nnz_a) + 1) & ~size_t(1);
     case AR_PVAL: return (size_t(P.nnz_p) + 1) & ~size_t(1);
     case AR_DINV: case AR_LSUB: return nb * bs * ld;
     case AR_IDX: return (size_t(P.idx_entries) * sizeof(idx_t) + 7) / 8;
-    case AR_BORDER: return ((np * nb * bs + 1) & ~size_t(1)) + np * (np + 1) + ((bs * ld + 1) & ~size_t(1)) +
-                           ((np * bs + 1) & ~size_t(1)) + ((np + 2) & ~size_t(1)) + 66;
+    case AR_LP: return (np * nb * bs + 1) & ~size_t(1);
+    case AR_SCRATCH: return 3 * np * (np + 1) + 2 * ((bs * ld + 1) & ~size_t(1)) + 2 * ((np * bs + 1) & ~size_t(1)) +
+                            ((np + 2) & ~size_t(1)) + 64;
     default: return 0;
   }
 }
@@ -78,13 +89,14 @@ __host__ __device__ inline size_t slab_doubles_for(const PatternDev& P, uint32_t
 
 // kAllSmem: every array is in shared memory (the plan's mask has all bits set); the pointers are
 // then derived from the shared-memory base only, which lets the compiler emit LDS/STS.
-template <bool kAllSmem>
+template <int kPlace>
 __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t smem_mask, double* sm, double* gl) {
   double* ptr[AR_COUNT];
 #pragma unroll
   for (int id = 0; id < AR_COUNT; ++id) {
     const size_t sz = (array_doubles(P, id) + 1) & ~size_t(1);
-    if (kAllSmem || (smem_mask >> id & 1u)) { ptr[id] = sm; sm += sz; }
+    const bool in_smem = kPlace == PLACE_SMEM ? true : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (smem_mask >> id & 1u) != 0);
+    if (in_smem) { ptr[id] = sm; sm += sz; }
     else { ptr[id] = gl; gl += sz; }
   }
   W.x = ptr[AR_X]; W.q = ptr[AR_Q]; W.b = ptr[AR_B]; W.z = ptr[AR_Z]; W.y = ptr[AR_Y]; W.l = ptr[AR_L]; W.u = ptr[AR_U];
@@ -92,14 +104,18 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
   W.Aval = ptr[AR_AVAL]; W.Dinv = ptr[AR_DINV]; W.Lsub = ptr[AR_LSUB];
   W.idx = reinterpret_cast<idx_t*>(ptr[AR_IDX]);
   W.Pval = ptr[AR_PVAL];
-  const size_t np = P.tri_np, N = size_t(P.tri_nb) * P.tri_bs;
-  double* bp = ptr[AR_BORDER];
-  W.Lp = bp; bp += (np * N + 1) & ~size_t(1);
+  const size_t np = P.tri_np;
+  W.Lp = ptr[AR_LP];
+  double* bp = ptr[AR_SCRATCH];
   W.Dp = bp; bp += np * (np + 1);
-  W.S = bp; bp += (size_t(P.tri_bs) * P.tri_ld + 1) & ~size_t(1);
-  W.Sp = bp; bp += (np * P.tri_bs + 1) & ~size_t(1);
+  W.Dp2 = bp; bp += 2 * np * (np + 1);
+  W.s_stride = static_cast<int>((size_t(P.tri_bs) * P.tri_ld + 1) & ~size_t(1));
+  W.sp_stride = static_cast<int>((np * P.tri_bs + 1) & ~size_t(1));
+  W.S = bp; bp += 2 * W.s_stride;
+  W.Sp = bp; bp += 2 * W.sp_stride;
   W.xp = bp; bp += (np + 2) & ~size_t(1);
   W.piv = bp;
+  W.w = ptr[AR_W];
   W.D = ptr[AR_D]; W.E = ptr[AR_E]; W.dx = ptr[AR_DX]; W.dy = ptr[AR_DY];
 }
 
@@ -358,18 +374,19 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
 }  // namespace direct
 }  // namespace ocpb200
 #include "tri_fast.cuh"
+#include "tri_twisted.cuh"
 namespace ocpb200 {
 namespace direct {
 
 // block-size dispatch (uniform across the CTA)
 __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work& W) {
-  if (P.tri_bs == 16) tri_factor_exact<16>(P, W);
-  else if (P.tri_bs == 20) tri_factor_exact<20>(P, W);
+  if (P.tri_bs == 16) tri_factor_twisted<16>(P, W);
+  else if (P.tri_bs == 20) tri_factor_twisted<20>(P, W);
   else tri_factor(P, W);
 }
 __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
-  if (P.tri_bs == 16) tri_solve_exact<16>(P, W);
-  else if (P.tri_bs == 20) tri_solve_exact<20>(P, W);
+  if (P.tri_bs == 16) tri_solve_twisted<16>(P, W);
+  else if (P.tri_bs == 20) tri_solve_twisted<20>(P, W);
   else tri_solve(P, W);
 }
 
@@ -382,6 +399,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
   const int n = P.n, m = P.m;
   const double sigma = S.sigma, relax = S.relax;
   PhaseClock clk(A.phase);
+  const_cast<Work&>(W).phase = A.phase;
 
   // ---- load (osqp_setup copies its inputs): values, q, bounds clamped to +-1e30 ------------
   {
@@ -399,7 +417,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
       if (lo > hi) bad[0] = 1.0;
       W.l[i] = fmax(lo, -kInfty);
       W.u[i] = fmin(hi, kInfty);
-      W.E[i] = 1.0; W.z[i] = 0.0; W.y[i] = 0.0;
+      W.E[i] = 1.0; W.z[i] = 0.0; W.y[i] = 0.0; W.w[i] = 0.0;
     }
     block_reduce<1, true>(bad, R);
     if (bad[0] > 0.0) {  // osqp_setup rejects l > u; the reference then adds no usable step
@@ -414,12 +432,15 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
   for (int pass = 0; pass < S.scaling_iters; ++pass) {
     for (int j = tid; j < n; j += T) {
       double dn = 0.0;
+#pragma unroll 4
       for (int k = P.p_colptr[j]; k < P.p_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Pval[k]));
+#pragma unroll 4
       for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Aval[k]));
       W.b[j] = 1.0 / sqrt(limit_scaling(dn));
     }
     for (int i = tid; i < m; i += T) {
       double en = 0.0;
+#pragma unroll 4
       for (int k = P.a_rowptr[i]; k < P.a_rowptr[i + 1]; ++k) en = fmax(en, fabs(W.Aval[P.a_perm[k]]));
       W.dy[i] = 1.0 / sqrt(limit_scaling(en));
     }
@@ -433,6 +454,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
         W.Pval[k] = v;
         cn = fmax(cn, fabs(v));
       }
+#pragma unroll 4
       for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) W.Aval[k] *= W.dy[P.a_rowidx[k]] * dj;
       const double qj = W.q[j] * dj;
       W.q[j] = qj;
@@ -479,12 +501,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
     // ---- right-hand side of the reduced KKT system: sigma x - q + A'(rho z - y) --------------
     for (int j = tid; j < n; j += T) {
       double s = sigma * W.x[j] - W.q[j];
-      const int e = P.a_colptr[j + 1];
-      for (int k = P.a_colptr[j]; k < e; ++k) {
-        const int r = P.a_rowidx[k];
-        s += W.Aval[k] * (rv.of(W.ctype[r]) * W.z[r] - W.y[r]);
-      }
-      W.b[j] = s;
+      W.b[j] = s + col_dot_A(P, W.Aval, W.w, j);
     }
     __syncthreads();
     clk.lap(OCP_B200_PHASE_RHS);
@@ -503,8 +520,10 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
       const double zr = relax * zt + (1.0 - relax) * W.z[i];
       const double zn = fmin(fmax(zr + rv.inv(ct) * W.y[i], W.l[i]), W.u[i]);
       const double dy = rh * (zr - zn);
-      W.y[i] += dy;
+      const double yn = W.y[i] + dy;
+      W.y[i] = yn;
       W.z[i] = zn;
+      W.w[i] = rh * zn - yn;
       if (want_info) W.dy[i] = dy;
     });
     for (int j = tid; j < n; j += T) {
@@ -644,6 +663,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
         rho = est;
         ++rho_updates;
         rv = Rho(rho);
+        for (int i = tid; i < m; i += T) W.w[i] = rv.of(W.ctype[i]) * W.z[i] - W.y[i];
         tri_assemble(P, W, rv, sigma);
         factor_dispatch(P, W);
       }
@@ -664,17 +684,17 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
 }
 
 // persistent kernel: CTAs pull instances from A.counter
-template <bool kAllSmem>
-__global__ void __launch_bounds__(kDirectThreads, 1)
+template <int kPlace, int kThreads, int kBlocksPerSm>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm)
 admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArgs A, const uint32_t smem_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double red_buf[2 * (kDirectThreads / 32) * kRedWidth];
+  __shared__ double red_buf[2 * (kThreads / 32) * kRedWidth];
   __shared__ int s_inst;
   Work W;
-  carve<kAllSmem>(W, P, smem_mask, reinterpret_cast<double*>(smem_raw),
-                  kAllSmem ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles);
+  carve<kPlace>(W, P, smem_mask, reinterpret_cast<double*>(smem_raw),
+                kPlace == PLACE_SMEM ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles);
   PatternDev PL = P;
-  if (kAllSmem || (smem_mask >> AR_IDX & 1u)) {
+  if (kPlace != PLACE_MIXED || (smem_mask >> AR_IDX & 1u)) {
     // index structures move into shared memory once per CTA (same offsets as the global arena)
     for (int k = threadIdx.x; k < P.idx_entries; k += blockDim.x) W.idx[k] = P.idx_base[k];
     auto move = [&](const idx_t*& ptr) { ptr = W.idx + (ptr - P.idx_base); };
@@ -682,7 +702,7 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
     move(PL.p_colptr); move(PL.p_rowidx); move(PL.rows_long); move(PL.rows_short);
     __syncthreads();
   }
-  Reducer R{red_buf, 0, (kDirectThreads / 32) * kRedWidth};
+  Reducer R{red_buf, 0, (kThreads / 32) * kRedWidth};
   while (true) {
     if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
     __syncthreads();

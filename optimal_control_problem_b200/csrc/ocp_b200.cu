@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -47,6 +48,8 @@ int fail(int code, const std::string& msg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                         \
   } while (0)
 
+#define RC_TRY(expr) do { int rc_ = (expr); if (rc_ != OCP_B200_OK) return rc_; } while (0)
+
 using ocpb200::idx_t;
 using ocpb200::PatternDev;
 using ocpb200::SolveArgs;
@@ -76,6 +79,12 @@ int pad8(int v) { return (v + 7) & ~7; }
 
 }  // namespace
 
+struct LaunchPlan {
+  int place = 0, threads = 256, smem_bytes = 0, max_ctas = 1;
+  uint32_t smem_mask = 0;
+  size_t slab_doubles = 0;
+};
+
 struct ocp_b200_solver {
   // problem
   int np = 0, nf = 0, horizon = 0, ng = 0, n = 0, m = 0, N = 0, nnz_h = 0, nnz_a = 0, nnz_p = 0;
@@ -94,6 +103,8 @@ struct ocp_b200_solver {
   int num_sms = 0, threads = 512, resident = 0, smem_bytes = 0, max_ctas = 0;
   size_t slab_doubles = 0;
   int use_direct = 0;          // 1: admm_direct_kernel (block-tridiagonal LDL'), 0: PCG kernel
+  int place = 0;               // direct kernel: ocpb200::direct::Placement of the throughput plan
+  LaunchPlan deep, wide;       // latency plan (1 CTA/SM) and throughput plan (2 CTAs/SM)
   uint32_t smem_mask = 0;      // direct kernel: which state arrays live in shared memory
   // workspaces (device)
   DevBuf<double> hv, q, av, l, u, solx, soly, info, slab, trace;
@@ -253,29 +264,61 @@ int plan_launch(ocp_b200_solver* s) {
   int per_sm = 1;
   if (s->use_direct) {
     namespace D = ocpb200::direct;
-    s->threads = D::block_threads();
-    D::KernelInfo ki{};
-    CUDA_TRY(D::kernel_info(true, &ki));
-    D::KernelInfo ki2{};
-    CUDA_TRY(D::kernel_info(false, &ki2));
-    const int stat = std::max(ki.static_smem, ki2.static_smem);
-    size_t avail = (size_t(max_optin) - stat) / sizeof(double), used = 0, slab = 0;
-    uint32_t mask = 0;
     const int count = D::plan_array_count();
+    // Two plans are kept.  `wide`: 2 CTAs per SM (vectors, A values, index arrays and scratch in
+    // shared memory, factor blocks in an L2-resident slab) -- the throughput plan, used when the
+    // batch has more instances than SMs.  `deep`: 1 CTA per SM with as much state as fits in shared
+    // memory (everything, for the H=20 quadrotor) -- the latency plan, used for small batches.
+    // OCP_B200_PLAN = smem | multi | mixed forces one of them (diagnostics).
+    const char* env = std::getenv("OCP_B200_PLAN");
+    size_t multi_smem = 0, multi_slab = 0, all = 0;
     for (int id = 0; id < count; ++id) {
       const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
-      if (used + sz <= avail) { mask |= 1u << id; used += sz; }
-      else slab += sz;
+      all += sz;
+      (D::plan_multi_in_smem(id) ? multi_smem : multi_slab) += sz;
     }
-    s->smem_mask = mask;
-    s->smem_bytes = static_cast<int>(used * sizeof(double));
-    s->resident = mask == (1u << count) - 1u ? 1 : 0;
-    s->slab_doubles = (slab + 15) & ~size_t(15);
-    // the attribute is per function, not per handle: always opt in to the maximum so that handles
-    // of different problems can coexist in one process
-    CUDA_TRY(D::set_max_dynamic_smem(true, max_optin - stat));
-    CUDA_TRY(D::set_max_dynamic_smem(false, max_optin - stat));
-    CUDA_TRY(D::occupancy(s->resident != 0, s->threads, s->smem_bytes, &per_sm));
+    auto make_plan = [&](int place, LaunchPlan& L) -> int {
+      D::KernelInfo kx{};
+      CUDA_TRY(D::kernel_info(place, &kx));
+      L.place = place;
+      L.threads = kx.threads;
+      CUDA_TRY(D::set_max_dynamic_smem(place, max_optin - kx.static_smem));
+      if (place == 2) {
+        L.smem_mask = 0;
+        L.smem_bytes = static_cast<int>(multi_smem * sizeof(double));
+        L.slab_doubles = (multi_slab + 15) & ~size_t(15);
+      } else {
+        size_t avail = (size_t(max_optin) - kx.static_smem) / sizeof(double), used = 0, slab = 0;
+        uint32_t mask = 0;
+        for (int id = 0; id < count; ++id) {
+          const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
+          if (place == 1 || used + sz <= avail) { mask |= 1u << id; used += sz; }
+          else slab += sz;
+        }
+        L.smem_mask = mask;
+        L.smem_bytes = static_cast<int>(used * sizeof(double));
+        L.slab_doubles = (slab + 15) & ~size_t(15);
+      }
+      int occ = 1;
+      CUDA_TRY(D::occupancy(place, L.smem_bytes, &occ));
+      L.max_ctas = std::max(1, occ) * s->num_sms;
+      return OCP_B200_OK;
+    };
+    D::KernelInfo ki{}, km{};
+    CUDA_TRY(D::kernel_info(1, &ki));
+    CUDA_TRY(D::kernel_info(2, &km));
+    const bool fits_all = all * sizeof(double) + ki.static_smem <= size_t(max_optin);
+    const bool fits_multi = (multi_smem * sizeof(double) + km.static_smem + 1024) * 2 <= size_t(228) * 1024;
+    int deep = fits_all ? 1 : 0, wide = fits_multi ? 2 : deep;
+    if (env && !std::strcmp(env, "multi") && fits_multi) deep = wide = 2;
+    else if (env && !std::strcmp(env, "mixed")) deep = wide = 0;
+    else if (env && !std::strcmp(env, "smem") && fits_all) deep = wide = 1;
+    RC_TRY(make_plan(deep, s->deep));
+    RC_TRY(make_plan(wide, s->wide));
+    s->place = s->wide.place; s->threads = s->wide.threads; s->smem_bytes = s->wide.smem_bytes;
+    s->smem_mask = s->wide.smem_mask; s->slab_doubles = s->wide.slab_doubles;
+    s->resident = s->deep.place == 1 ? 1 : 0;
+    per_sm = s->wide.max_ctas / s->num_sms;
   } else {
     s->threads = 512;
     const size_t idx_entries = size_t(pad8(P.n + 1)) * 2 + size_t(pad8(P.nnz_a)) * 3 + pad8(P.m + 1) + pad8(P.nnz_p) +
@@ -353,16 +396,18 @@ int launch_admm(ocp_b200_solver* s, SolveArgs& A, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
   A.counter = s->counter.p;
   A.phase = s->profiling ? s->phase.p : nullptr;
-  const int grid = std::min(A.B, s->max_ctas);
+  int grid = std::min(A.B, s->max_ctas);
   ProfScope prof(s, OCP_B200_PROF_ADMM, st);
   if (s->use_direct) {
-    A.slab = nullptr; A.slab_doubles = s->slab_doubles;
-    if (!s->resident) {
-      CUDA_TRY(s->slab.reserve(size_t(grid) * s->slab_doubles));
+    // small batches (at most one instance per SM): the latency plan; otherwise the throughput plan
+    const LaunchPlan& L = A.B <= s->num_sms ? s->deep : s->wide;
+    grid = std::min(A.B, L.max_ctas);
+    A.slab = nullptr; A.slab_doubles = L.slab_doubles;
+    if (L.slab_doubles > 0) {
+      CUDA_TRY(s->slab.reserve(size_t(grid) * L.slab_doubles));
       A.slab = s->slab.p;
     }
-    CUDA_TRY(ocpb200::direct::launch(s->resident != 0, grid, s->threads, s->smem_bytes, st, s->pat, s->settings, A,
-                                     s->smem_mask));
+    CUDA_TRY(ocpb200::direct::launch(L.place, grid, L.smem_bytes, st, s->pat, s->settings, A, L.smem_mask));
   } else if (s->resident) {
     A.slab = nullptr; A.slab_doubles = 0;
     ocp_b200_settings t = s->settings;
@@ -412,7 +457,6 @@ int d2h(double* dst, const double* src, size_t count, cudaStream_t st) {
   return OCP_B200_OK;
 }
 
-#define RC_TRY(expr) do { int rc_ = (expr); if (rc_ != OCP_B200_OK) return rc_; } while (0)
 
 int upload_problem_inputs(ocp_b200_solver* s, int B, const double* frames, const double* p, const double* lbx,
                           const double* ubx, const double* lbg, const double* ubg, cudaStream_t st) {
@@ -735,7 +779,7 @@ int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int*
   if (nnz_h) *nnz_h = s->nnz_h;
   if (nnz_a) *nnz_a = s->nnz_a;
   if (smem_bytes) *smem_bytes = s->smem_bytes;
-  if (resident) *resident = s->resident | (s->use_direct << 1);
+  if (resident) *resident = s->resident | (s->use_direct << 1) | (s->place << 2);
   return OCP_B200_OK;
 }
 

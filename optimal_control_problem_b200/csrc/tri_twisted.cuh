@@ -1,0 +1,242 @@
+// tri_twisted.cuh -- "burn at both ends" (twisted) variant of the bordered block-tridiagonal
+// LDL' of admm_direct_kernel.cuh, exact block size BS.
+//
+// The factorisation and the two sweeps of a solve are sequential in the block index, and one
+// warp cannot go faster than its dependent-instruction chain.  The twisted ordering eliminates
+// blocks 0, 1, ..., mid-1 from the top and nb-1, nb-2, ..., mid+1 from the bottom AT THE SAME
+// TIME (two thread groups / two warps), and block mid last.  Same storage, no extra fill, half
+// the sequential depth:
+//     top    k = 1..mid      L_k = K_{k,k-1} D_{k-1}^-1      D_k -= L_k K_{k,k-1}'
+//     bottom k = nb-2..mid   U_k = K_{k,k+1} D_{k+1}^-1      D_k -= U_k K_{k+1,k}
+// Slot s of the sub-diagonal storage (which starts out as K_{s,s-1}) ends up holding L_s for
+// s <= mid and U_{s-1} for s > mid.  The border rows (reference parameters) follow either
+// chain with the same recurrences:  V_k -= V_pred C',  L_p,pred = V_pred D_pred^-1,
+// D_p -= V_pred L_p,pred', where C is the coupling block just computed.
+#pragma once
+
+namespace ocpb200 {
+namespace direct {
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// One elimination step of a chain, executed by a thread group (gt of GT threads, barrier `bar`):
+//   C  = slot content: K_{s,s-1}; the step owns block k, the previously eliminated neighbour is `pred`
+//   kTop: k = s, pred = s - 1, coupling = C Dinv_pred;  else: k = s - 1, pred = s, coupling = C' Dinv_pred
+// Updates D_k (not inverted here), V_k, finalises L_p,pred, accumulates into Dpacc, overwrites the slot.
+template <int BS, bool kTop>
+__device__ __forceinline__ void chain_step(const Work& W, int np, int N, int ld, int k, int pred, int slot, double* S,
+                                           double* Sp, double* Dpacc, int gt, int GT, int bar) {
+  constexpr int bb = BS * BS;
+  const int pb = np * BS;
+  double* C = W.Lsub + size_t(slot) * BS * ld;
+  double* Dk = W.Dinv + size_t(k) * BS * ld;
+  const double* Dm = W.Dinv + size_t(pred) * BS * ld;   // D_pred^-1 (symmetric)
+  // coupling block into S; V_pred into Sp
+  for (int e = gt; e < bb; e += GT) {
+    const int r = e / BS, c = e % BS;
+    S[r * ld + c] = kTop ? dot_cc<BS>(C + r * ld, Dm + c * ld) : dot_cs<BS>(Dm + c * ld, C + r, ld);
+  }
+  for (int e = gt; e < pb; e += GT) {
+    const int r = e / BS, c = e % BS;
+    Sp[e] = W.Lp[size_t(r) * N + pred * BS + c];
+  }
+  group_barrier(bar, GT);
+  // D_k -= coupling * K_{pred,k};  V_k -= V_pred coupling';  L_p,pred = V_pred D_pred^-1
+  for (int e = gt; e < bb; e += GT) {
+    const int r = e / BS, c = e % BS;
+    Dk[r * ld + c] -= kTop ? dot_cc<BS>(S + r * ld, C + c * ld) : dot_cs<BS>(S + r * ld, C + c, ld);
+  }
+  for (int e = gt; e < pb; e += GT) {
+    const int r = e / BS, c = e % BS;
+    const double s = dot_cc<BS>(Sp + r * BS, S + c * ld);
+    const double f = dot_cc<BS>(Sp + r * BS, Dm + c * ld);
+    W.Lp[size_t(r) * N + k * BS + c] -= s;
+    W.Lp[size_t(r) * N + pred * BS + c] = f;
+  }
+  group_barrier(bar, GT);
+  // D_p accumulator += V_pred L_p,pred';  slot <- coupling
+  for (int e = gt; e < np * np; e += GT) {
+    const int r = e / np, c = e - r * np;
+    Dpacc[r * (np + 1) + c] += dot_cs<BS>(Sp + r * BS, W.Lp + size_t(c) * N + pred * BS, 1);
+  }
+  for (int e = gt; e < bb; e += GT) {
+    const int r = e / BS, c = e % BS;
+    C[r * ld + c] = S[r * ld + c];
+  }
+  group_barrier(bar, GT);
+}
+
+template <int BS>
+__device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+  const int np = P.tri_np, nb = P.tri_nb, ld = P.tri_ld, N = nb * BS;
+  const int mid = nb / 2;
+  const int GT = T / 2;                    // two thread groups of whole warps
+  const int grp = tid >= GT ? 1 : 0, gt = tid - grp * GT;
+  double* S = W.S + grp * W.s_stride;
+  double* Sp = W.Sp + grp * W.sp_stride;
+  double* piv = W.piv + grp * 32;
+  double* Dpacc = W.Dp2 + grp * np * (np + 1);
+  for (int e = gt; e < np * (np + 1); e += GT) Dpacc[e] = 0.0;
+  // both chains: invert the chain's current block, then eliminate into the next one
+  if (grp == 0) {
+    for (int k = 0; k < mid; ++k) {           // blocks 0..mid-1; step into k+1 (the last one is mid)
+      if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
+      group_barrier(1, GT);
+      chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1);
+    }
+  } else {
+    for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
+      if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
+      group_barrier(2, GT);
+      chain_step<BS, false>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2);
+    }
+    if (mid + 1 < nb) {                       // block mid+1: inverted here, eliminated into mid below
+      if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid + 1) * BS * ld, ld, lane, piv);
+      group_barrier(2, GT);
+    }
+  }
+  __syncthreads();
+  // the bottom chain's last step lands on block mid as well: run it with the whole CTA
+  if (mid + 1 < nb) chain_step<BS, false>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0);
+  if (tid < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid) * BS * ld, ld, lane, W.piv);
+  __syncthreads();
+  // border of the last block, then D_p = K_pp - (accumulated) - V_mid L_p,mid', inverted
+  if (np > 0) {
+    const double* Dm = W.Dinv + size_t(mid) * BS * ld;
+    const int pb = np * BS;
+    for (int e = tid; e < pb; e += T) {
+      const int r = e / BS, c = e % BS;
+      W.Sp[e] = W.Lp[size_t(r) * N + mid * BS + c];
+    }
+    __syncthreads();
+    for (int e = tid; e < pb; e += T) {
+      const int r = e / BS, c = e % BS;
+      W.Lp[size_t(r) * N + mid * BS + c] = dot_cc<BS>(W.Sp + r * BS, Dm + c * ld);
+    }
+    __syncthreads();
+    for (int e = tid; e < np * np; e += T) {
+      const int r = e / np, c = e - r * np;
+      const int o = r * (np + 1) + c;
+      W.Dp[o] -= W.Dp2[o] + W.Dp2[np * (np + 1) + o] +
+                 dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + mid * BS, 1);
+    }
+    __syncthreads();
+    if (tid < 32) warp_invert(W.Dp, np, np + 1, lane);
+    __syncthreads();
+  }
+}
+
+// `count` consecutive sweep stages by one warp: stage i multiplies slot (slot0 + i*dslot) with
+// source block (src0 + i*dblk) and subtracts from destination block (dst0 + i*dblk).
+// kColumn = false: dst[r] -= sum_c M[r][c] src[c]   (forward sweeps)
+// kColumn = true : dst[r] -= sum_c M[c][r] src[c]   (backward sweeps)
+template <int BS, bool kColumn>
+__device__ __forceinline__ void run_chain(const Work& W, double* bx, int ld, int slot0, int dslot, int dst0, int src0,
+                                          int dblk, int count, int lane) {
+  constexpr int CPL = TriCfg<BS>::CPL, LPR = TriCfg<BS>::LPR;
+  const int row = lane / LPR, half = lane % LPR;
+  const bool act = row < BS;
+  const int rr = act ? row : 0;
+  const bool writer = act && half == 0;
+  auto load = [&](double (&dst)[CPL], int slot) {
+    if (!kColumn) {
+      const double2* p = reinterpret_cast<const double2*>(W.Lsub + size_t(slot) * BS * ld + rr * ld + half * CPL);
+#pragma unroll
+      for (int i = 0; i < CPL / 2; ++i) { const double2 v = p[i]; dst[2 * i] = v.x; dst[2 * i + 1] = v.y; }
+    } else {
+      const double* p = W.Lsub + size_t(slot) * BS * ld + size_t(half * CPL) * ld + rr;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) dst[i] = p[i * ld];
+    }
+  };
+  if (count <= 0) return;
+  double La[CPL], Lb[CPL];
+  load(La, slot0);
+  for (int i = 0; i < count; i += 2) {
+    if (i + 1 < count) load(Lb, slot0 + (i + 1) * dslot);
+    sweep_stage<BS>(La, bx + (src0 + i * dblk) * BS + half * CPL, bx + (dst0 + i * dblk) * BS + rr, writer);
+    if (i + 1 < count) {
+      if (i + 2 < count) load(La, slot0 + (i + 2) * dslot);
+      sweep_stage<BS>(Lb, bx + (src0 + (i + 1) * dblk) * BS + half * CPL, bx + (dst0 + (i + 1) * dblk) * BS + rr, writer);
+    }
+  }
+}
+
+// K x = b in place: b is [p | block 0 | ... | block nb-1]
+template <int BS>
+__device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int np = P.tri_np, nb = P.tri_nb, ld = P.tri_ld, N = nb * BS;
+  const int mid = nb / 2;
+  double* bx = W.b + np;
+  PhaseClock clk(W.phase);
+  // forward: top chain y_k = b_k - L_k y_{k-1} (k = 1..mid-1) and bottom chain
+  // y_k = b_k - U_k y_{k+1} (k = nb-2..mid+1) on two warps, then both contributions to block mid
+  if (warp == 0) run_chain<BS, false>(W, bx, ld, 1, 1, 1, 0, 1, mid - 1, lane);
+  else if (warp == 1) run_chain<BS, false>(W, bx, ld, nb - 1, -1, nb - 2, nb - 1, -1, nb - 2 - mid, lane);
+  __syncthreads();
+  if (warp == 0) {
+    if (mid >= 1) run_chain<BS, false>(W, bx, ld, mid, 1, mid, mid - 1, 1, 1, lane);
+    if (mid + 1 < nb) run_chain<BS, false>(W, bx, ld, mid + 1, 1, mid, mid + 1, 1, 1, lane);
+  }
+  __syncthreads();
+  clk.lap(OCP_B200_PHASE_SOLVE_FWD);
+  // border: y_p = b_p - sum_k L_pk y_k  (a warp per border row), x_p = D_p^-1 y_p
+  if (np > 0) {
+    for (int r = warp; r < np; r += nw) {
+      const double* rowp = W.Lp + size_t(r) * N;
+      double s0 = 0.0, s1 = 0.0;
+      int j = lane;
+      for (; j + 32 < N; j += 64) { s0 = fma(rowp[j], bx[j], s0); s1 = fma(rowp[j + 32], bx[j + 32], s1); }
+      if (j < N) s0 = fma(rowp[j], bx[j], s0);
+      double s = s0 + s1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) W.xp[r] = W.b[r] - s;
+    }
+    __syncthreads();
+    if (tid < np) {
+      double s = 0.0;
+      for (int c = 0; c < np; ++c) s = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s);
+      W.b[tid] = s;
+    }
+    __syncthreads();
+  }
+  clk.lap(OCP_B200_PHASE_SOLVE_BORDER);
+  // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
+  {
+    const int Tb = (T / BS) * BS;   // whole blocks per pass: a pass never reads what it overwrites
+    const int k1 = tid / BS, r1 = tid % BS, kstep = T / BS;
+    for (int base = 0, k = k1; base < N; base += Tb, k += kstep) {
+      const int j = tid < Tb ? base + tid : N;
+      double v = 0.0;
+      if (j < N) {
+        v = dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
+        double v1 = 0.0;
+        int p = 0;
+        for (; p + 1 < np; p += 2) {
+          v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+          v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
+        }
+        if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+        v += v1;
+      }
+      __syncthreads();
+      if (j < N) bx[j] = v;
+    }
+  }
+  __syncthreads();
+  clk.lap(OCP_B200_PHASE_SOLVE_DIAG);
+  // backward, from block mid outwards: x_k = c_k - L_{k+1}' x_{k+1} (k = mid-1..0) and
+  // x_k = c_k - U_{k-1}' x_{k-1} (k = mid+1..nb-1)
+  if (warp == 0) run_chain<BS, true>(W, bx, ld, mid, -1, mid - 1, mid, -1, mid, lane);
+  else if (warp == 1) run_chain<BS, true>(W, bx, ld, mid + 1, 1, mid + 1, mid, 1, nb - 1 - mid, lane);
+  __syncthreads();
+  clk.lap(OCP_B200_PHASE_SOLVE_BWD);
+}
+
+}  // namespace direct
+}  // namespace ocpb200
