@@ -18,6 +18,19 @@ constexpr int kMaxWarps = 32;
 
 typedef uint16_t idx_t;
 
+// K-assembly program (direct kernel): one entry per structurally non-zero element of the bordered
+// block-tridiagonal K = P + sigma I + A' diag(rho) A that has to be computed, with the products
+// sum_r rho_r A_ri A_rj encoded as RUNS of consecutive positions in columns i and j of A whose rows
+// coincide one-to-one (host-side merge of the two sorted columns, done once per pattern).
+struct KRun { uint16_t ka, kc, len, pad; };
+struct KEntry {
+  uint32_t dest0, dest1;   // (array << 30) | offset; array 0 = Dinv, 1 = Lsub, 2 = Lp, 3 = Dp; dest1 = mirror or 0xffffffff
+  int32_t ppos;            // position of P_ij in the symmetrised P values, or -1
+  uint32_t run_begin;      // first run in the run array
+  uint16_t nruns, diag;    // diag != 0: i == j (sigma is added)
+  uint32_t pad;
+};
+
 // Index structures of one sparsity pattern (device pointers, shared by every instance)
 struct PatternDev {
   int n, m, nnz_a, nnz_p, nnz_h;
@@ -27,6 +40,9 @@ struct PatternDev {
   // columns [0, tri_np) form the border (the reference parameters p), then tri_nb diagonal
   // blocks of tri_bs columns each; block rows are stored with an even pitch tri_ld >= tri_bs + 1
   int tri_ok, tri_np, tri_bs, tri_nb, tri_ld;
+  int kprog_entries;       // K-assembly program (null / 0: assemble by merging columns on the device)
+  const KEntry* kprog;
+  const KRun* kruns;
   int idx_entries;         // length of the idx_t arena (every array padded to 8 entries)
   const idx_t* idx_base;   // start of the arena
   const idx_t* a_colptr;   // n+1

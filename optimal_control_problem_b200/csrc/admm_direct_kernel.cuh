@@ -158,7 +158,43 @@ __device__ __forceinline__ double k_entry(const PatternDev& P, const Work& W, co
   return s;
 }
 
+// K assembly from the host-built program (PatternDev::kprog): zero the factor storage, then one
+// thread per structurally non-zero element walks its runs of matching A entries.  Same summation
+// order as the merging version below (sigma, P_ij, then products by ascending row).
+__device__ inline void tri_assemble_program(const PatternDev& P, const Work& W, const Rho& rho, double sigma) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
+  {
+    const int nfac = nb * bs * ld;   // even (ld is even)
+    double2* d2 = reinterpret_cast<double2*>(W.Dinv);
+    double2* l2 = reinterpret_cast<double2*>(W.Lsub);
+    const double2 z = make_double2(0.0, 0.0);
+    for (int e = tid; e < nfac / 2; e += T) { d2[e] = z; l2[e] = z; }
+    for (int e = tid; e < np * N; e += T) W.Lp[e] = 0.0;
+    for (int e = tid; e < np * (np + 1); e += T) W.Dp[e] = 0.0;
+  }
+  __syncthreads();
+  double* const arr[4] = {W.Dinv, W.Lsub, W.Lp, W.Dp};
+  for (int e = tid; e < P.kprog_entries; e += T) {
+    const KEntry ent = P.kprog[e];
+    double s = ent.diag ? sigma : 0.0;
+    if (ent.ppos >= 0) s += W.Pval[ent.ppos];
+    for (int q = 0; q < ent.nruns; ++q) {
+      const KRun run = P.kruns[ent.run_begin + q];
+#pragma unroll 4
+      for (int t = 0; t < run.len; ++t) {
+        const int ka = run.ka + t, kc = run.kc + t;
+        s += rho.of(W.ctype[P.a_rowidx[ka]]) * W.Aval[ka] * W.Aval[kc];
+      }
+    }
+    arr[ent.dest0 >> 30][ent.dest0 & 0x3fffffffu] = s;
+    if (ent.dest1 != 0xffffffffu) arr[ent.dest1 >> 30][ent.dest1 & 0x3fffffffu] = s;
+  }
+  __syncthreads();
+}
+
 __device__ inline void tri_assemble(const PatternDev& P, const Work& W, const Rho& rho, double sigma) {
+  if (P.kprog_entries > 0) { tri_assemble_program(P, W, rho, sigma); return; }
   const int tid = threadIdx.x, T = blockDim.x;
   const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
   const int bb = bs * bs;

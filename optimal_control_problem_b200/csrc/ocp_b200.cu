@@ -95,6 +95,8 @@ struct ocp_b200_solver {
   PatternDev pat{};
   DevBuf<idx_t> d_idx;
   DevBuf<int> d_int;
+  DevBuf<ocpb200::KEntry> d_kent;
+  DevBuf<ocpb200::KRun> d_krun;
   // stage library
   void* lib = nullptr;
   model_assemble_fn assemble = nullptr;
@@ -250,6 +252,66 @@ int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
       if (hi >= 0 && hi - lo > 1) ok = false;
     }
     P.tri_ok = ok ? 1 : 0;
+    P.kprog_entries = 0; P.kprog = nullptr; P.kruns = nullptr;
+    if (ok) {
+      // K-assembly program: every element of the factor storage that can be non-zero
+      const int ld = P.tri_ld, N = nb * bs, np = s->np;
+      std::vector<ocpb200::KEntry> ents;
+      std::vector<ocpb200::KRun> runs;
+      auto add = [&](int i, int j, uint32_t d0, uint32_t d1) {
+        ocpb200::KEntry e{};
+        e.dest0 = d0; e.dest1 = d1; e.ppos = -1; e.run_begin = static_cast<uint32_t>(runs.size()); e.nruns = 0;
+        e.diag = i == j ? 1 : 0; e.pad = 0;
+        for (int k = pc[j]; k < pc[j + 1]; ++k)
+          if (pr[k] == i) { e.ppos = k; break; }
+        int ka = ac[i], kc = ac[j];
+        const int ea = ac[i + 1], ec = ac[j + 1];
+        while (ka < ea && kc < ec) {
+          if (ar[ka] == ar[kc]) {
+            if (e.nruns > 0 && runs.back().ka + runs.back().len == ka && runs.back().kc + runs.back().len == kc) {
+              runs.back().len++;
+            } else {
+              runs.push_back({static_cast<uint16_t>(ka), static_cast<uint16_t>(kc), 1, 0});
+              e.nruns++;
+            }
+            ++ka; ++kc;
+          } else if (ar[ka] < ar[kc]) ++ka;
+          else ++kc;
+        }
+        if (e.nruns > 0 || e.ppos >= 0 || e.diag) ents.push_back(e);
+      };
+      const uint32_t none = 0xffffffffu;
+      auto dst = [](uint32_t arr, size_t off) { return (arr << 30) | static_cast<uint32_t>(off); };
+      bool fits = size_t(nb) * bs * ld < (1u << 30) && size_t(np) * N < (1u << 30);
+      if (fits) {
+        for (int k = 0; k < nb; ++k)
+          for (int r = 0; r < bs; ++r)
+            for (int c = r; c < bs; ++c)
+              add(np + k * bs + r, np + k * bs + c, dst(0, size_t(k) * bs * ld + r * ld + c),
+                  r == c ? none : dst(0, size_t(k) * bs * ld + c * ld + r));
+        for (int k = 1; k < nb; ++k)
+          for (int r = 0; r < bs; ++r)
+            for (int c = 0; c < bs; ++c)
+              add(np + k * bs + r, np + (k - 1) * bs + c, dst(1, size_t(k) * bs * ld + r * ld + c), none);
+        for (int r = 0; r < np; ++r)
+          for (int j = 0; j < N; ++j) add(r, np + j, dst(2, size_t(r) * N + j), none);
+        for (int r = 0; r < np; ++r)
+          for (int c = r; c < np; ++c)
+            add(r, c, dst(3, size_t(r) * (np + 1) + c), r == c ? none : dst(3, size_t(c) * (np + 1) + r));
+        // longest entries first: threads take entries round-robin, so the tail stays short
+        std::stable_sort(ents.begin(), ents.end(), [&](const ocpb200::KEntry& a, const ocpb200::KEntry& b) {
+          auto len = [&](const ocpb200::KEntry& e) { int t = 0; for (int q = 0; q < e.nruns; ++q) t += runs[e.run_begin + q].len; return t; };
+          return len(a) > len(b);
+        });
+        CUDA_TRY(s->d_kent.reserve(ents.size()));
+        CUDA_TRY(s->d_krun.reserve(runs.size()));
+        CUDA_TRY(cudaMemcpy(s->d_kent.p, ents.data(), ents.size() * sizeof(ocpb200::KEntry), cudaMemcpyHostToDevice));
+        if (!runs.empty())
+          CUDA_TRY(cudaMemcpy(s->d_krun.p, runs.data(), runs.size() * sizeof(ocpb200::KRun), cudaMemcpyHostToDevice));
+        P.kprog_entries = static_cast<int>(ents.size());
+        P.kprog = s->d_kent.p; P.kruns = s->d_krun.p;
+      }
+    }
   }
   return OCP_B200_OK;
 }
@@ -553,7 +615,7 @@ int ocp_b200_destroy(ocp_b200_solver* s) {
   if (!s) return OCP_B200_OK;
   cudaSetDevice(s->device);
   if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
-  s->d_idx.release(); s->d_int.release();
+  s->d_idx.release(); s->d_int.release(); s->d_kent.release(); s->d_krun.release();
   DevBuf<double>* bufs[] = {&s->hv, &s->q, &s->av, &s->l, &s->u, &s->solx, &s->soly, &s->info, &s->slab, &s->trace,
                             &s->x, &s->p, &s->frames, &s->lbx, &s->ubx, &s->lbg, &s->ubg, &s->f, &s->stats};
   for (DevBuf<double>* b : bufs) b->release();
