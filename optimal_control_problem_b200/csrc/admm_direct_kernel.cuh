@@ -48,7 +48,9 @@ enum ArrayId {
   AR_X = 0, AR_Q, AR_B, AR_Z, AR_Y, AR_L, AR_U, AR_CTYPE, AR_W, AR_AVAL, AR_SCRATCH, AR_IDX, AR_DINV, AR_LSUB, AR_PVAL,
   AR_LP, AR_D, AR_E, AR_DX, AR_DY, AR_COUNT
 };
-__host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX; }
+// throughput plan: vectors, A values, scratch, index arrays + the small set-up / check vectors in
+// shared memory (107 KB for the quadrotor, two CTAs per SM); the factor blocks in the global slab
+__host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX || id == AR_PVAL || id >= AR_D; }
 
 struct Work {
   double *x, *q, *b, *z, *y, *l, *u;
