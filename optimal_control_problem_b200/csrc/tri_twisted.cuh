@@ -184,24 +184,42 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   }
   __syncthreads();
   clk.lap(OCP_B200_PHASE_SOLVE_FWD);
-  // border: y_p = b_p - sum_k L_pk y_k  (a warp per border row), x_p = D_p^-1 y_p
+  // border: y_p = b_p - sum_k L_pk y_k  (half a warp per border row, loads issued in batches of 8
+  // so that a slab-resident L_p costs one L2 latency per batch), x_p = D_p^-1 y_p
   if (np > 0) {
-    for (int r = warp; r < np; r += nw) {
-      const double* rowp = W.Lp + size_t(r) * N;
+    const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
+    for (int r0 = 0; r0 < np; r0 += nhw) {
+      const int r = r0 + hw;
+      const bool have = r < np;
+      const double* rowp = W.Lp + size_t(have ? r : 0) * N;
       double s0 = 0.0, s1 = 0.0;
-      int j = lane;
-      for (; j + 32 < N; j += 64) { s0 = fma(rowp[j], bx[j], s0); s1 = fma(rowp[j + 32], bx[j + 32], s1); }
-      if (j < N) s0 = fma(rowp[j], bx[j], s0);
+      for (int j0 = hl; j0 < N; j0 += 128) {
+        double lv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 16 * u;
+          const bool ok = have && j < N;
+          lv[u] = ok ? rowp[j] : 0.0;
+          yv[u] = ok ? bx[j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) { s0 = fma(lv[u], yv[u], s0); s1 = fma(lv[u + 1], yv[u + 1], s1); }
+      }
       double s = s0 + s1;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) W.xp[r] = W.b[r] - s;
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (have && hl == 0) W.xp[r] = W.b[r] - s;
     }
     __syncthreads();
     if (tid < np) {
-      double s = 0.0;
-      for (int c = 0; c < np; ++c) s = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s);
-      W.b[tid] = s;
+      double s0 = 0.0, s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < np; c += 2) {
+        s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
+        s1 = fma(W.Dp[tid * (np + 1) + c + 1], W.xp[c + 1], s1);
+      }
+      if (c < np) s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
+      W.b[tid] = s0 + s1;
     }
     __syncthreads();
   }

@@ -178,6 +178,30 @@ def test_infeasible_step_propagates_nan(problems, native):
     assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
 
 
+def test_throughput_plan_matches_oracle_and_latency_plan(problems, native):
+    """Batches larger than the SM count run the 2-CTA/SM plan (factor blocks in an L2 slab), small
+    batches the all-shared-memory plan: same arithmetic, so the same bits -- and the oracle's answer."""
+    prob, ora = problems("quadrotor")
+    B = 400
+    frames, refs = prob.sample_inputs(B, 0xB200 + 5)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = 0.1, 4
+    prob.solver.update_settings(s)
+    x = np.zeros((B, prob.N)); st = np.zeros((B, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, None, st)
+    pick = [0, 147, 148, 295, 296, 399]
+    for b in pick:
+        xb = np.zeros((1, prob.N))
+        prob.solver.solve_batch(frames[b:b + 1], refs[b:b + 1], prob.lbx, prob.ubx, prob.lbg, prob.ubg, xb)
+        assert np.array_equal(xb[0], x[b])
+    ora.set_schedule(4, 0.1)
+    ora.set_qp_settings(_oracle.settings_from_b200(s))
+    ox, of, ost = ora.solve_batch(frames[pick], refs[pick])
+    assert rel_err(x[pick], ox) < REL_SOLUTION
+    assert np.array_equal(st[pick][:, native.STAT["admm_iters"]], ost[:, 2])
+    assert (st[:, native.STAT["qp_status"]] == native.QP_SOLVED).all()
+
+
 def test_batch_equals_single_instance(problems, native):
     """Every instance of a batch gets the bits it gets when solved alone."""
     prob, _ = problems("quadrotor")
