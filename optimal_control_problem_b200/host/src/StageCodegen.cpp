@@ -385,7 +385,10 @@ ModelSource generate(const ModelSpec& spec) {
   s << "constexpr int NX = " << N << ", NVAR = " << n << ", NCON = " << m << ";\n";
   s << "constexpr int NNZ_H = " << hr.size() << ", NNZ_A = " << ar.size() << ";\n";
   s << "constexpr int NUM_GROUPS = " << G << ", STAGE_A = " << stage_a << ", STAGE_H = " << stage_h << ";\n";
-  s << "constexpr int WARPS_PER_BLOCK = 4;\n\n";
+  // resident blocks per SM the assembly kernel is compiled for (register cap = 65536 / (128 * blocks))
+  int min_blocks = 4;   // measured on B200 (quadrotor, B=4096): 1.20 ms at 2, 0.94 at 3, 0.89 at 4
+  if (const char* e = std::getenv("OCP_B200_ASSEMBLE_MIN_BLOCKS")) min_blocks = std::max(1, std::atoi(e));
+  s << "constexpr int WARPS_PER_BLOCK = 4, MIN_BLOCKS = " << min_blocks << ";\n\n";
   s << "struct GroupInfo { int tmpl, otmpl, first_col, ncols, xoff, a_base, a_len, h_base, h_len, atab_off, "
        "htab_off, ctab_off; };\n";
   s << "__constant__ GroupInfo c_groups[NUM_GROUPS] = {\n";
@@ -428,7 +431,7 @@ __device__ __forceinline__ void copy_out(double* __restrict__ dst, const double*
   }
   s << R"(
 // one warp per (instance, column group)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS)
 assemble_kernel(const int B, const double* __restrict__ x, const double* __restrict__ p,
                 const double* __restrict__ frames, const double* __restrict__ lbx, const double* __restrict__ ubx,
                 const double* __restrict__ lbg, const double* __restrict__ ubg, double* __restrict__ hv, const int ldh,
@@ -563,8 +566,10 @@ std::string compile(const ModelSource& src, const std::string& name, const std::
   const char* nvcc_env = std::getenv("OCP_B200_NVCC");
   const std::string nvcc = nvcc_env ? nvcc_env : "nvcc";
   const std::string tmp = so + ".tmp." + std::to_string(static_cast<long>(::getpid()));
+  const char* extra_env = std::getenv("OCP_B200_NVCC_FLAGS");
+  const std::string extra = extra_env ? std::string(" ") + extra_env : std::string();
   const std::string cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared "
-                          "-Xcompiler -fPIC -I" + include_dir() + " -o " + tmp + " " + cu + " 2>&1";
+                          "-Xcompiler -fPIC" + extra + " -I" + include_dir() + " -o " + tmp + " " + cu + " 2>&1";
   if (verbose) std::cout << "compiling stage library: " << cmd << std::endl;
   FILE* pipe = popen(cmd.c_str(), "r");
   if (!pipe) throw std::runtime_error("codegen: cannot start nvcc");

@@ -58,6 +58,15 @@ def test_no_device_is_an_error_not_a_fallback(native):
         prob.compute_optimal_trajectory(np.zeros(prob.nf), np.zeros(prob.np_))
 
 
+def test_problem_too_large_for_16_bit_indices_is_unsupported(native):
+    """Maximum size: index structures are 16-bit, n + ng must stay below 65535 (checked before any device work)."""
+    n = 70000
+    hc = np.arange(n + 1, dtype=np.int32); hr = np.arange(n, dtype=np.int32)
+    with pytest.raises(native.OcpB200Error) as e:
+        native.Solver.create(n, n, hc, hr, hc, hr)
+    assert e.value.code == 5   # OCP_B200_ERR_UNSUPPORTED
+
+
 def test_invalid_descriptions_are_rejected(native):
     for args in [dict(n=2, m=3, hc=[0, 1, 1], hr=[0], ac=[0, 1, 3], ar=[0, 2, 1]),   # rows not increasing
                  dict(n=2, m=3, hc=[0, 1, 2], hr=[0, 1], ac=[0, 1], ar=[0])]:          # colptr too short -> nnz mismatch

