@@ -302,3 +302,48 @@ def test_empty_batch_and_bad_arguments(problems, native):
     assert lib.ocp_b200_solve_batch(prob.solver.handle, 2, None, None, None, None, None, None, None, None, None) == 1
     assert b"bad arguments" in lib.ocp_b200_last_error()
     assert lib.ocp_b200_solve_batch(None, 1, None, None, None, None, None, None, None, None, None) == 1
+
+
+def _cartpole_yaml(verbose, gen_code, alpha=1.0, steps=6, horizon=8):
+    return f"""
+optimal_control_problem:
+  discretization_settings:
+    dt: 0.01
+    horizon: {horizon}
+  solver_settings:
+    max_iter: 1000
+    warm_start: true
+    verbose: {str(verbose).lower()}
+    gen_code: {str(gen_code).lower()}
+    load_lib: false
+    solve_method: CUDA_SQP
+    SQP_settings:
+      alpha: {alpha}
+      step_num: {steps}
+  OCP_variables:
+    - name: state
+      size: 4
+      lower_bound: [-2.4, -.inf, -.inf, -.inf]
+      upper_bound: [2.4, .inf, .inf, .inf]
+    - name: force
+      size: 1
+      lower_bound: [-20.0]
+      upper_bound: [20.0]
+"""
+
+
+def test_verbose_mode_and_gen_code(native, capfd):
+    """verbose: true steps one SQP iteration at a time with the reference's verbose-only early exit
+    (||dx||_2 < 1e-6, SQPOptimizationSolver.cpp:183-197); without convergence it must give the same
+    iterate as the silent path.  gen_code: true serialises localSystemFunction (:403-425)."""
+    from pathlib import Path
+    quiet = native.Problem("cartpole", yaml_text=_cartpole_yaml(False, True))
+    loud = native.Problem("cartpole", yaml_text=_cartpole_yaml(True, False))
+    frame = np.array([0.05, 0.2, 0.0, 0.1, 0.0]); ref = np.zeros(4)
+    xq, fq = quiet.compute_optimal_trajectory(frame, ref)
+    xl, fl = loud.compute_optimal_trajectory(frame, ref)
+    out = capfd.readouterr().out
+    assert "SQP start" in out and "step 1/6" in out
+    assert np.allclose(xq, xl, rtol=0, atol=1e-9)
+    saved = Path(native.SHARE_DIR) / "code_gen" / "localSystemFunction.casadi"
+    assert saved.exists() and saved.stat().st_size > 1000
