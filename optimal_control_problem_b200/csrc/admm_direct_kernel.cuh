@@ -418,13 +418,14 @@ namespace direct {
 
 // block-size dispatch (uniform across the CTA)
 __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work& W) {
-  if (P.tri_bs == 16) tri_factor_twisted<16>(P, W);
-  else if (P.tri_bs == 20) tri_factor_twisted<20>(P, W);
+  // exact-size code assumes the pitch tri_ld == bs + 2 (what the host sets for even block sizes)
+  if (P.tri_bs == 16 && P.tri_ld == 18) tri_factor_twisted<16>(P, W);
+  else if (P.tri_bs == 20 && P.tri_ld == 22) tri_factor_twisted<20>(P, W);
   else tri_factor(P, W);
 }
 __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
-  if (P.tri_bs == 16) tri_solve_twisted<16>(P, W);
-  else if (P.tri_bs == 20) tri_solve_twisted<20>(P, W);
+  if (P.tri_bs == 16 && P.tri_ld == 18) tri_solve_twisted<16>(P, W);
+  else if (P.tri_bs == 20 && P.tri_ld == 22) tri_solve_twisted<20>(P, W);
   else tri_solve(P, W);
 }
 

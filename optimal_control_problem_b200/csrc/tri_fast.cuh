@@ -58,7 +58,8 @@ __device__ __forceinline__ double dot_cs(const double* __restrict__ a, const dou
 // in-place inverse of an SPD BS x BS block (Gauss-Jordan, no pivoting) by ONE warp.
 // Lane c < BS holds column c in registers; `piv` is a 16-byte aligned scratch of >= BS doubles.
 template <int BS>
-__device__ __forceinline__ void warp_invert_exact(double* M, int ld, int lane, double* piv) {
+__device__ __forceinline__ void warp_invert_exact(double* M, int /*ld*/, int lane, double* piv) {
+  constexpr int ld = BS + 2;
   const bool act = lane < BS;
   const int cc = act ? lane : 0;
   double col[BS];

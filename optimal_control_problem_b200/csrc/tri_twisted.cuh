@@ -26,9 +26,9 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 //   kTop: k = s, pred = s - 1, coupling = C Dinv_pred;  else: k = s - 1, pred = s, coupling = C' Dinv_pred
 // Updates D_k (not inverted here), V_k, finalises L_p,pred, accumulates into Dpacc, overwrites the slot.
 template <int BS, bool kTop>
-__device__ __forceinline__ void chain_step(const Work& W, int np, int N, int ld, int k, int pred, int slot, double* S,
+__device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*ld*/, int k, int pred, int slot, double* S,
                                            double* Sp, double* Dpacc, int gt, int GT, int bar) {
-  constexpr int bb = BS * BS;
+  constexpr int bb = BS * BS, ld = BS + 2;   // compile-time pitch: addresses fold into immediates
   const int pb = np * BS;
   double* C = W.Lsub + size_t(slot) * BS * ld;
   double* Dk = W.Dinv + size_t(k) * BS * ld;
@@ -71,7 +71,8 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int ld,
 template <int BS>
 __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
-  const int np = P.tri_np, nb = P.tri_nb, ld = P.tri_ld, N = nb * BS;
+  const int np = P.tri_np, nb = P.tri_nb, N = nb * BS;
+  constexpr int ld = BS + 2;   // == P.tri_ld for even BS (checked by the dispatcher)
   const int mid = nb / 2;
   const int GT = T / 2;                    // two thread groups of whole warps
   const int grp = tid >= GT ? 1 : 0, gt = tid - grp * GT;
@@ -134,9 +135,9 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
 // kColumn = false: dst[r] -= sum_c M[r][c] src[c]   (forward sweeps)
 // kColumn = true : dst[r] -= sum_c M[c][r] src[c]   (backward sweeps)
 template <int BS, bool kColumn>
-__device__ __forceinline__ void run_chain(const Work& W, double* bx, int ld, int slot0, int dslot, int dst0, int src0,
+__device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/, int slot0, int dslot, int dst0, int src0,
                                           int dblk, int count, int lane) {
-  constexpr int CPL = TriCfg<BS>::CPL, LPR = TriCfg<BS>::LPR;
+  constexpr int CPL = TriCfg<BS>::CPL, LPR = TriCfg<BS>::LPR, ld = BS + 2;
   const int row = lane / LPR, half = lane % LPR;
   const bool act = row < BS;
   const int rr = act ? row : 0;
@@ -169,7 +170,8 @@ __device__ __forceinline__ void run_chain(const Work& W, double* bx, int ld, int
 template <int BS>
 __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-  const int np = P.tri_np, nb = P.tri_nb, ld = P.tri_ld, N = nb * BS;
+  const int np = P.tri_np, nb = P.tri_nb, N = nb * BS;
+  constexpr int ld = BS + 2;
   const int mid = nb / 2;
   double* bx = W.b + np;
   PhaseClock clk(W.phase);
