@@ -178,6 +178,7 @@ template <int BS>
 __device__ __forceinline__ void sweep_stage(const double (&Lpart)[TriCfg<BS>::CPL], const double* __restrict__ src,
                                             double* __restrict__ dst, bool writer) {
   constexpr int CPL = TriCfg<BS>::CPL, LPR = TriCfg<BS>::LPR;
+  const double old = writer ? *dst : 0.0;   // issued before the chain, not after the shuffle
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
   for (int c = 0; c < CPL; c += 4) {
@@ -188,7 +189,7 @@ __device__ __forceinline__ void sweep_stage(const double (&Lpart)[TriCfg<BS>::CP
   double s = (s0 + s1) + (s2 + s3);
   if (LPR >= 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
   if (LPR >= 4) s += __shfl_xor_sync(0xffffffffu, s, 2);
-  if (writer) *dst -= s;
+  if (writer) *dst = old - s;
   __syncwarp();
 }
 

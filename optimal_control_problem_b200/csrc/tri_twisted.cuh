@@ -142,27 +142,32 @@ __device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/,
   const bool act = row < BS;
   const int rr = act ? row : 0;
   const bool writer = act && half == 0;
-  auto load = [&](double (&dst)[CPL], int slot) {
+  if (count <= 0) return;
+  // everything advances by pointer increments: no per-stage multiplications in the single warp's stream
+  const double* lp = W.Lsub + size_t(slot0) * BS * ld + (kColumn ? size_t(half * CPL) * ld + rr : size_t(rr) * ld + half * CPL);
+  const int dl = dslot * BS * ld, db = dblk * BS;
+  const double* srcp = bx + src0 * BS + half * CPL;
+  double* dstp = bx + dst0 * BS + rr;
+  auto load = [&](double (&dst)[CPL], const double* p) {
     if (!kColumn) {
-      const double2* p = reinterpret_cast<const double2*>(W.Lsub + size_t(slot) * BS * ld + rr * ld + half * CPL);
+      const double2* p2 = reinterpret_cast<const double2*>(p);
 #pragma unroll
-      for (int i = 0; i < CPL / 2; ++i) { const double2 v = p[i]; dst[2 * i] = v.x; dst[2 * i + 1] = v.y; }
+      for (int i = 0; i < CPL / 2; ++i) { const double2 v = p2[i]; dst[2 * i] = v.x; dst[2 * i + 1] = v.y; }
     } else {
-      const double* p = W.Lsub + size_t(slot) * BS * ld + size_t(half * CPL) * ld + rr;
 #pragma unroll
       for (int i = 0; i < CPL; ++i) dst[i] = p[i * ld];
     }
   };
-  if (count <= 0) return;
   double La[CPL], Lb[CPL];
-  load(La, slot0);
+  load(La, lp);
   for (int i = 0; i < count; i += 2) {
-    if (i + 1 < count) load(Lb, slot0 + (i + 1) * dslot);
-    sweep_stage<BS>(La, bx + (src0 + i * dblk) * BS + half * CPL, bx + (dst0 + i * dblk) * BS + rr, writer);
+    if (i + 1 < count) load(Lb, lp + dl);
+    sweep_stage<BS>(La, srcp, dstp, writer);
     if (i + 1 < count) {
-      if (i + 2 < count) load(La, slot0 + (i + 2) * dslot);
-      sweep_stage<BS>(Lb, bx + (src0 + (i + 1) * dblk) * BS + half * CPL, bx + (dst0 + (i + 1) * dblk) * BS + rr, writer);
+      if (i + 2 < count) load(La, lp + 2 * dl);
+      sweep_stage<BS>(Lb, srcp + db, dstp + db, writer);
     }
+    lp += 2 * dl; srcp += 2 * db; dstp += 2 * db;
   }
 }
 
