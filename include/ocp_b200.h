@@ -199,7 +199,7 @@ long long ocp_b200_launch_count(const ocp_b200_solver* s);
 int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled);
 /* While profiling is on, CTA 0 of the direct kernel also accumulates SM cycles per phase of the
  * QP solves it runs (clock64 on one thread); get_phase_cycles returns and clears them. */
-#define OCP_B200_NPHASE 12
+#define OCP_B200_NPHASE 14
 #define OCP_B200_PHASE_LOAD         0
 #define OCP_B200_PHASE_SCALE        1  /* Ruiz equilibration                        */
 #define OCP_B200_PHASE_KKT_ASSEMBLE 2  /* K = P + sigma I + A' rho A into blocks    */
@@ -213,6 +213,9 @@ int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled);
 #define OCP_B200_PHASE_SOLVE_BORDER 9
 #define OCP_B200_PHASE_SOLVE_DIAG  10
 #define OCP_B200_PHASE_SOLVE_BWD   11
+/* finer split of PHASE_FACTOR (top chain of the twisted factorisation) */
+#define OCP_B200_PHASE_FACTOR_INVERT 12
+#define OCP_B200_PHASE_FACTOR_STEP   13
 int ocp_b200_get_phase_cycles(ocp_b200_solver* s, long long* cycles);
 int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int reset);
 /* dimensions of a handle: n, m, nnz_h, nnz_a, dynamic shared memory bytes per CTA, and

@@ -259,10 +259,10 @@ class Solver:
 
     def get_phase_cycles(self) -> dict:
         """SM cycles per QP phase accumulated by CTA 0 of the direct kernel while profiling was on."""
-        c = (C.c_longlong * 12)()
+        c = (C.c_longlong * 14)()
         _check(cuda_lib().ocp_b200_get_phase_cycles(self._h, c))
         return dict(zip(("load", "scale", "kkt_assemble", "factor", "rhs", "solve", "update", "check",
-                         "solve_fwd", "solve_border", "solve_diag", "solve_bwd"), list(c)))
+                         "solve_fwd", "solve_border", "solve_diag", "solve_bwd", "factor_invert", "factor_step"), list(c)))
 
     def device_dims(self) -> dict:
         v = [C.c_int() for _ in range(6)]

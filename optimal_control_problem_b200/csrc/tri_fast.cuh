@@ -56,30 +56,31 @@ __device__ __forceinline__ double dot_cs(const double* __restrict__ a, const dou
 }
 
 // in-place inverse of an SPD BS x BS block (Gauss-Jordan, no pivoting) by ONE warp.
-// Lane c < BS holds column c in registers; `piv` is a 16-byte aligned scratch of >= BS doubles.
-template <int BS>
+// Lane c < BS holds column c in registers.  Per pivot k the multipliers f[r] = -M[r][k] / M[k][k]
+// are needed by every lane; M[r][k] is (up to the sign flip of already pivoted rows) element k of
+// lane r's own column, because the working matrix stays symmetric among unpivoted indices:
+// lane k broadcasts 1 / M[k][k] (one shuffle), every lane forms its own f[r] with one multiply and
+// the 16 values are all-gathered through `piv` (16-byte aligned scratch of >= BS doubles).  The
+// serial part of a pivot is reciprocal -> shuffle -> multiply -> store/load round trip -> FMAs.
+template <int BS, int LD = BS + 2>
 __device__ __forceinline__ void warp_invert_exact(double* M, int /*ld*/, int lane, double* piv) {
-  constexpr int ld = BS + 2;
+  constexpr int ld = LD;
+  static_assert(BS % 2 == 0 && BS <= 32, "one column per lane, even size");
   const bool act = lane < BS;
   const int cc = act ? lane : 0;
   double col[BS];
 #pragma unroll
   for (int r = 0; r < BS; ++r) col[r] = M[r * ld + cc];
-  double2* piv2 = reinterpret_cast<double2*>(piv);
+  const double2* piv2 = reinterpret_cast<const double2*>(piv);
 #pragma unroll
   for (int k = 0; k < BS; ++k) {
-    if (lane == k) {
-      // multipliers of this pivot: f'[r] = -M[r][k] / M[k][k], and 1 / M[k][k] in slot k
-      const double ipiv = 1.0 / col[k];
-      double f[BS];
-#pragma unroll
-      for (int r = 0; r < BS; ++r) f[r] = (r == k) ? ipiv : -col[r] * ipiv;
-#pragma unroll
-      for (int r = 0; r < BS / 2; ++r) piv2[r] = make_double2(f[2 * r], f[2 * r + 1]);
-    }
-    __syncwarp();
-    const double ck = col[k];
+    const double ck = col[k];                                   // M[k][c] == M[c][k]
+    const double ipiv = 1.0 / __shfl_sync(0xffffffffu, ck, k);  // every lane: 1 / M[k][k]
     const bool mine = lane == k;
+    // f[lane] = -M[lane][k] / M[k][k].  Rows already pivoted hold the sign-flipped coupling
+    // (M[r][k] == -M[k][r] for r < k in in-place Gauss-Jordan), rows still to come are symmetric.
+    if (act) piv[lane] = mine ? ipiv : (lane < k ? ck * ipiv : -ck * ipiv);
+    __syncwarp();
 #pragma unroll
     for (int r = 0; r < BS / 2; ++r) {
       const double2 f = piv2[r];
@@ -93,6 +94,14 @@ __device__ __forceinline__ void warp_invert_exact(double* M, int /*ld*/, int lan
 #pragma unroll
     for (int r = 0; r < BS; ++r) M[r * ld + lane] = col[r];
   }
+}
+
+// D_p^-1 (np x np, pitch np + 1): exact-size code for the border sizes of the benchmark problems
+__device__ __forceinline__ void invert_border(double* Dp, int np, int lane, double* piv) {
+  if (np == 12) warp_invert_exact<12, 13>(Dp, 13, lane, piv);
+  else if (np == 4) warp_invert_exact<4, 5>(Dp, 5, lane, piv);
+  else if (np == 24) warp_invert_exact<24, 25>(Dp, 25, lane, piv);
+  else warp_invert(Dp, np, np + 1, lane);
 }
 
 template <int BS>

@@ -83,10 +83,13 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   for (int e = gt; e < np * (np + 1); e += GT) Dpacc[e] = 0.0;
   // both chains: invert the chain's current block, then eliminate into the next one
   if (grp == 0) {
+    PhaseClock clk(W.phase);
     for (int k = 0; k < mid; ++k) {           // blocks 0..mid-1; step into k+1 (the last one is mid)
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(1, GT);
+      clk.lap(OCP_B200_PHASE_FACTOR_INVERT);
       chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1);
+      clk.lap(OCP_B200_PHASE_FACTOR_STEP);
     }
   } else {
     for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
@@ -125,7 +128,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
                  dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + mid * BS, 1);
     }
     __syncthreads();
-    if (tid < 32) warp_invert(W.Dp, np, np + 1, lane);
+    if (tid < 32) invert_border(W.Dp, np, lane, W.piv);
     __syncthreads();
   }
 }

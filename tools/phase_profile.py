@@ -23,6 +23,6 @@ sol.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, None, s
 dt = time.time() - t
 print(name, "B", B, "wall ms", round(dt * 1e3, 2), sol.get_profile(), sol.device_dims())
 ph = sol.get_phase_cycles()
-tot = max(1, sum(v for k, v in ph.items() if not k.startswith("solve_")))
+tot = max(1, sum(v for k, v in ph.items() if not k.startswith(("solve_", "factor_"))))
 print({k: (v, round(100 * v / tot, 1)) for k, v in ph.items()}, "total cycles", tot, "admm iters inst0", st[0, 2],
       "qps", st[0, 1])
