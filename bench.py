@@ -84,7 +84,7 @@ def reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample or max(64, 8 * threads)
+    sample = args.cpu_sample or max(64, 32 * threads)
     times = cpu_run(sample, threads, repeats=args.steps, warmup=args.warmup)
     total = sum(times)
     value = sample * args.steps / total
@@ -314,7 +314,7 @@ def b200_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_sample or max(64, 16 * threads)
+        sample = args.cpu_sample or max(64, 64 * threads)   # ~20 core-seconds of CPU work
         t = cpu_run(sample, threads, repeats=1, warmup=0)[0]
         t1 = cpu_run(min(sample, 32), 1, repeats=1, warmup=0)[0] / min(sample, 32)
         cpu = {"value": sample / t, "unit": UNIT, "cores": threads, "kind": "port",
