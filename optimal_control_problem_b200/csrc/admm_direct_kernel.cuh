@@ -82,15 +82,8 @@ __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
   }
 }
 
-__host__ __device__ inline size_t slab_doubles_for(const PatternDev& P, uint32_t smem_mask) {
-  size_t tot = 0;
-  for (int id = 0; id < AR_COUNT; ++id)
-    if (!(smem_mask >> id & 1u)) tot += (array_doubles(P, id) + 1) & ~size_t(1);
-  return tot;
-}
-
-// kAllSmem: every array is in shared memory (the plan's mask has all bits set); the pointers are
-// then derived from the shared-memory base only, which lets the compiler emit LDS/STS.
+// With a compile-time placement (PLACE_SMEM / PLACE_MULTI) every pointer is derived from exactly
+// one base, so the compiler knows its address space and emits LDS/STS or LDG/STG, not generic LD.
 template <int kPlace>
 __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t smem_mask, double* sm, double* gl) {
   double* ptr[AR_COUNT];
@@ -247,6 +240,34 @@ __device__ __forceinline__ void warp_invert(double* M, int bs, int ld, int lane)
   }
 }
 
+// in-place inverse of an SPD bs x bs block (Gauss-Jordan, no pivoting) by the WHOLE CTA, staged
+// through a shared-memory scratch block (the block itself may live in the global slab).  Generic
+// in bs; three barriers per pivot.  The exact-size one-warp version is in tri_fast.cuh.
+__device__ inline void block_invert_coop(double* M, double* scratch, int bs, int ld) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int bb = bs * bs;
+  for (int e = tid; e < bs * ld; e += T) scratch[e] = M[e];
+  __syncthreads();
+  for (int k = 0; k < bs; ++k) {
+    const double ipiv = 1.0 / scratch[k * ld + k];
+    for (int e = tid; e < bb; e += T) {
+      const int r = e / bs, c = e - r * bs;
+      if (r != k && c != k) scratch[r * ld + c] -= scratch[r * ld + k] * (scratch[k * ld + c] * ipiv);
+    }
+    __syncthreads();
+    for (int c = tid; c < bs; c += T) {
+      if (c != k) {
+        scratch[k * ld + c] *= ipiv;
+        scratch[c * ld + k] *= -ipiv;
+      }
+    }
+    if (tid == 0) scratch[k * ld + k] = ipiv;
+    __syncthreads();
+  }
+  for (int e = tid; e < bs * ld; e += T) M[e] = scratch[e];
+  __syncthreads();
+}
+
 // block LDL' of the bordered block-tridiagonal K held in the factor storage
 __device__ inline void tri_factor(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -300,8 +321,7 @@ __device__ inline void tri_factor(const PatternDev& P, const Work& W) {
         Tk[r * ld + c] = W.S[r * ld + c];
       }
     }
-    if (warp == 0) warp_invert(Dk, bs, ld, lane);
-    __syncthreads();
+    block_invert_coop(Dk, W.S + W.s_stride, bs, ld);   // second scratch set: phase 3 may still read the first
   }
   // last border block, then D_p^-1
   if (np > 0) {
@@ -330,33 +350,71 @@ __device__ inline void tri_factor(const PatternDev& P, const Work& W) {
   }
 }
 
+// Generic block sweep for any block size bs <= 64 (the exact-size code in tri_fast.cuh /
+// tri_twisted.cuh covers bs = 16 and 20): four lanes per block row, the rows of a block spread
+// over ceil(4 bs / 32) warps that meet at a named barrier after every stage; each lane keeps the
+// next stage's slice of its row in registers (the factor may live in the global slab).
+//   kColumn = false: y_k -= L_k y_{k-1}, k = 1..nb-1        kColumn = true: x_k -= L_{k+1}' x_{k+1}, k = nb-2..0
+template <bool kColumn>
+__device__ __forceinline__ void coop_sweep(const PatternDev& P, const Work& W, double* bx) {
+  const int tid = threadIdx.x;
+  const int bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld;
+  const int nthr = ((4 * bs + 31) / 32) * 32;   // participating threads (whole warps)
+  if (tid >= nthr || nb < 2) return;
+  const int row = tid >> 2, sub = tid & 3;
+  const bool act = row < bs;
+  const int rr = act ? row : 0;
+  constexpr int kMaxPer = 16;                    // columns per lane: bs <= 64
+  const int per = (bs + 3) >> 2;
+  double cur[kMaxPer], nxt[kMaxPer];
+  auto load = [&](double (&dst)[kMaxPer], int slot) {
+    const double* base = W.Lsub + size_t(slot) * bs * ld;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+      const int c = sub + 4 * i;
+      dst[i] = (i < per && c < bs) ? (kColumn ? base[c * ld + rr] : base[rr * ld + c]) : 0.0;
+    }
+  };
+  const int first = kColumn ? nb - 1 : 1, step = kColumn ? -1 : 1;
+  load(cur, first);
+  for (int t = 0; t < nb - 1; ++t) {
+    const int slot = first + t * step;
+    const int dstb = kColumn ? slot - 1 : slot, srcb = kColumn ? slot : slot - 1;
+    if (t + 1 < nb - 1) load(nxt, slot + step);
+    const double* src = bx + srcb * bs;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; i += 2) {
+      const int c0 = sub + 4 * i, c1 = sub + 4 * (i + 1);
+      if (i < per && c0 < bs) s0 = fma(cur[i], src[c0], s0);
+      if (i + 1 < per && c1 < bs) s1 = fma(cur[i + 1], src[c1], s1);
+    }
+    double sum = s0 + s1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (act && sub == 0) bx[dstb * bs + row] -= sum;
+    asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) cur[i] = nxt[i];
+  }
+}
+
 // K x = b in place: b is [p | block 0 | ... | block nb-1]
 __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
   double* bx = W.b + np;
-  // forward sweep: y_k = b_k - L_k y_{k-1}   (one warp; lanes own rows)
-  if (warp == 0) {
-    for (int k = 1; k < nb; ++k) {
-      const double* Lk = W.Lsub + size_t(k) * bs * ld;
-      const double* yp = bx + (k - 1) * bs;
-      double* yk = bx + k * bs;
-      for (int r = lane; r < bs; r += 32) {
-        double s0 = 0.0, s1 = 0.0;
-        int c = 0;
-        for (; c + 1 < bs; c += 2) { s0 += Lk[r * ld + c] * yp[c]; s1 += Lk[r * ld + c + 1] * yp[c + 1]; }
-        if (c < bs) s0 += Lk[r * ld + c] * yp[c];
-        yk[r] -= s0 + s1;
-      }
-      __syncwarp();
-    }
-  }
+  PhaseClock clk(W.phase);
+  // forward sweep: y_k = b_k - L_k y_{k-1}
+  coop_sweep<false>(P, W, bx);
   __syncthreads();
+  clk.lap(OCP_B200_PHASE_SOLVE_FWD);
   // border: y_p = b_p - sum_k L_pk y_k  (a warp per border row), x_p = D_p^-1 y_p
   if (np > 0) {
     for (int r = warp; r < np; r += nw) {
       double s = 0.0;
       const double* row = W.Lp + size_t(r) * N;
+#pragma unroll 8
       for (int j = lane; j < N; j += 32) s += row[j] * bx[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -370,6 +428,7 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
     }
     __syncthreads();
   }
+  clk.lap(OCP_B200_PHASE_SOLVE_BORDER);
   // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
   const int Tb = (T / bs) * bs;   // whole blocks per pass: a pass never reads what it overwrites
   for (int base = 0; base < N; base += Tb) {
@@ -381,32 +440,22 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
       const double* yk = bx + k * bs;
       double s0 = 0.0, s1 = 0.0;
       int c = 0;
+#pragma unroll 4
       for (; c + 1 < bs; c += 2) { s0 += Dk[c] * yk[c]; s1 += Dk[c + 1] * yk[c + 1]; }
       if (c < bs) s0 += Dk[c] * yk[c];
       v = s0 + s1;
+#pragma unroll 8
       for (int p = 0; p < np; ++p) v -= W.Lp[size_t(p) * N + j] * W.b[p];
     }
     __syncthreads();
     if (j < N) bx[j] = v;
   }
   __syncthreads();
+  clk.lap(OCP_B200_PHASE_SOLVE_DIAG);
   // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}
-  if (warp == 0) {
-    for (int k = nb - 2; k >= 0; --k) {
-      const double* Ln = W.Lsub + size_t(k + 1) * bs * ld;
-      const double* xn = bx + (k + 1) * bs;
-      double* xk = bx + k * bs;
-      for (int r = lane; r < bs; r += 32) {
-        double s0 = 0.0, s1 = 0.0;
-        int c = 0;
-        for (; c + 1 < bs; c += 2) { s0 += Ln[c * ld + r] * xn[c]; s1 += Ln[(c + 1) * ld + r] * xn[c + 1]; }
-        if (c < bs) s0 += Ln[c * ld + r] * xn[c];
-        xk[r] -= s0 + s1;
-      }
-      __syncwarp();
-    }
-  }
+  coop_sweep<true>(P, W, bx);
   __syncthreads();
+  clk.lap(OCP_B200_PHASE_SOLVE_BWD);
 }
 
 }  // namespace direct

@@ -1,5 +1,6 @@
-// tri_fast.cuh -- exact-size (compile-time BS) versions of the bordered block-tridiagonal LDL'
-// factorisation and solve of admm_direct_kernel.cuh.
+// tri_fast.cuh -- exact-size (compile-time BS) building blocks of the bordered block-tridiagonal
+// LDL' of admm_direct_kernel.cuh: dot products, the one-warp block inverse, one sweep stage.
+// tri_twisted.cuh assembles them into the factorisation and the solve.
 //
 // The sequential parts of the algorithm (the two sweeps of a solve, the Gauss-Jordan inverse
 // of a diagonal block) run in ONE warp while the rest of the CTA waits, so what limits them is
@@ -104,83 +105,6 @@ __device__ __forceinline__ void invert_border(double* Dp, int np, int lane, doub
   else warp_invert(Dp, np, np + 1, lane);
 }
 
-template <int BS>
-__device__ inline void tri_factor_exact(const PatternDev& P, const Work& W) {
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int np = P.tri_np, nb = P.tri_nb, ld = P.tri_ld, N = nb * BS;
-  constexpr int bb = BS * BS;
-  const int pb = np * BS;
-  const int r1 = tid / BS, c1 = tid % BS;
-  const int rstep = T / BS, cstep = T % BS;   // advancing an element index by T
-  for (int k = 0; k < nb; ++k) {
-    double* Dk = W.Dinv + size_t(k) * BS * ld;
-    if (k > 0) {
-      double* Tk = W.Lsub + size_t(k) * BS * ld;               // K_{k,k-1}
-      const double* Dm = W.Dinv + size_t(k - 1) * BS * ld;     // D_{k-1}^-1 (symmetric)
-      // S = K_{k,k-1} D_{k-1}^-1  (= L_k; D^-1 symmetric: its row c is its column c);  Sp = V_{k-1}
-      for (int e = tid, r = r1, c = c1; e < bb; e += T) {
-        W.S[r * ld + c] = dot_cc<BS>(Tk + r * ld, Dm + c * ld);
-        r += rstep; c += cstep; if (c >= BS) { c -= BS; ++r; }
-      }
-      for (int e = tid, r = r1, c = c1; e < pb; e += T) {
-        W.Sp[e] = W.Lp[size_t(r) * N + (k - 1) * BS + c];
-        r += rstep; c += cstep; if (c >= BS) { c -= BS; ++r; }
-      }
-      __syncthreads();
-      // D_k = K_kk - S K_{k,k-1}';  V_k = K_pk - V_{k-1} S';  L_{p,k-1} = V_{k-1} D_{k-1}^-1
-      for (int e = tid, r = r1, c = c1; e < bb; e += T) {
-        Dk[r * ld + c] -= dot_cc<BS>(W.S + r * ld, Tk + c * ld);
-        r += rstep; c += cstep; if (c >= BS) { c -= BS; ++r; }
-      }
-      for (int e = tid, r = r1, c = c1; e < pb; e += T) {
-        const double s = dot_cc<BS>(W.Sp + r * BS, W.S + c * ld);
-        const double f = dot_cc<BS>(W.Sp + r * BS, Dm + c * ld);
-        W.Lp[size_t(r) * N + k * BS + c] -= s;
-        W.Lp[size_t(r) * N + (k - 1) * BS + c] = f;
-        r += rstep; c += cstep; if (c >= BS) { c -= BS; ++r; }
-      }
-      __syncthreads();
-    }
-    if (warp == 0) {
-      warp_invert_exact<BS>(Dk, ld, lane, W.piv);
-    } else if (k > 0) {
-      // the other warps, meanwhile: D_p -= V_{k-1} L_{p,k-1}';  L_k <- S
-      double* Tk = W.Lsub + size_t(k) * BS * ld;
-      const int t2 = tid - 32, T2 = T - 32;
-      for (int e = t2; e < np * np; e += T2) {
-        const int r = e / np, c = e - r * np;
-        W.Dp[r * (np + 1) + c] -= dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + (k - 1) * BS, 1);
-      }
-      for (int e = t2; e < bb; e += T2) {
-        const int r = e / BS, c = e % BS;
-        Tk[r * ld + c] = W.S[r * ld + c];
-      }
-    }
-    __syncthreads();
-  }
-  // last border block, then D_p^-1
-  if (np > 0) {
-    const double* Dm = W.Dinv + size_t(nb - 1) * BS * ld;
-    for (int e = tid, r = r1, c = c1; e < pb; e += T) {
-      W.Sp[e] = W.Lp[size_t(r) * N + (nb - 1) * BS + c];
-      r += rstep; c += cstep; if (c >= BS) { c -= BS; ++r; }
-    }
-    __syncthreads();
-    for (int e = tid, r = r1, c = c1; e < pb; e += T) {
-      W.Lp[size_t(r) * N + (nb - 1) * BS + c] = dot_cc<BS>(W.Sp + r * BS, Dm + c * ld);
-      r += rstep; c += cstep; if (c >= BS) { c -= BS; ++r; }
-    }
-    __syncthreads();
-    for (int e = tid; e < np * np; e += T) {
-      const int r = e / np, c = e - r * np;
-      W.Dp[r * (np + 1) + c] -= dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + (nb - 1) * BS, 1);
-    }
-    __syncthreads();
-    if (warp == 0) warp_invert(W.Dp, np, np + 1, lane);
-    __syncthreads();
-  }
-}
-
 // one stage of a sweep: dst[r] -= sum_c Lpart[c] * src[c] over this lane's CPL columns, combined
 // over the LPR lanes of the row
 template <int BS>
@@ -200,101 +124,6 @@ __device__ __forceinline__ void sweep_stage(const double (&Lpart)[TriCfg<BS>::CP
   if (LPR >= 4) s += __shfl_xor_sync(0xffffffffu, s, 2);
   if (writer) *dst = old - s;
   __syncwarp();
-}
-
-// K x = b in place: b is [p | block 0 | ... | block nb-1]
-template <int BS>
-__device__ inline void tri_solve_exact(const PatternDev& P, const Work& W) {
-  constexpr int CPL = TriCfg<BS>::CPL, LPR = TriCfg<BS>::LPR;
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-  const int np = P.tri_np, nb = P.tri_nb, ld = P.tri_ld, N = nb * BS;
-  double* bx = W.b + np;
-  const int row = lane / LPR, half = lane % LPR;
-  const bool act = row < BS;
-  const int rr = act ? row : 0;
-  const bool writer = act && half == 0;
-  // forward sweep: y_k = b_k - L_k y_{k-1}   (one warp; next stage's row prefetched in registers)
-  if (warp == 0 && nb > 1) {
-    auto load_row = [&](double (&dst)[CPL], int k) {
-      const double2* p = reinterpret_cast<const double2*>(W.Lsub + size_t(k) * BS * ld + rr * ld + half * CPL);
-#pragma unroll
-      for (int i = 0; i < CPL / 2; ++i) { const double2 v = p[i]; dst[2 * i] = v.x; dst[2 * i + 1] = v.y; }
-    };
-    double La[CPL], Lb[CPL];
-    load_row(La, 1);
-    for (int k = 1; k < nb; k += 2) {
-      if (k + 1 < nb) load_row(Lb, k + 1);
-      sweep_stage<BS>(La, bx + (k - 1) * BS + half * CPL, bx + k * BS + rr, writer);
-      if (k + 1 < nb) {
-        if (k + 2 < nb) load_row(La, k + 2);
-        sweep_stage<BS>(Lb, bx + k * BS + half * CPL, bx + (k + 1) * BS + rr, writer);
-      }
-    }
-  }
-  __syncthreads();
-  // border: y_p = b_p - sum_k L_pk y_k  (a warp per border row), x_p = D_p^-1 y_p
-  if (np > 0) {
-    for (int r = warp; r < np; r += nw) {
-      const double* rowp = W.Lp + size_t(r) * N;
-      double s0 = 0.0, s1 = 0.0;
-      int j = lane;
-      for (; j + 32 < N; j += 64) { s0 = fma(rowp[j], bx[j], s0); s1 = fma(rowp[j + 32], bx[j + 32], s1); }
-      if (j < N) s0 = fma(rowp[j], bx[j], s0);
-      double s = s0 + s1;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) W.xp[r] = W.b[r] - s;
-    }
-    __syncthreads();
-    if (tid < np) {
-      double s = 0.0;
-      for (int c = 0; c < np; ++c) s = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s);
-      W.b[tid] = s;
-    }
-    __syncthreads();
-  }
-  // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
-  {
-    const int Tb = (T / BS) * BS;   // whole blocks per pass: a pass never reads what it overwrites
-    const int k1 = tid / BS, r1 = tid % BS, kstep = T / BS;
-    for (int base = 0, k = k1; base < N; base += Tb, k += kstep) {
-      const int j = tid < Tb ? base + tid : N;
-      double v = 0.0;
-      if (j < N) {
-        v = dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
-        double v1 = 0.0;
-        int p = 0;
-        for (; p + 1 < np; p += 2) {
-          v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
-          v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
-        }
-        if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
-        v += v1;
-      }
-      __syncthreads();
-      if (j < N) bx[j] = v;
-    }
-  }
-  __syncthreads();
-  // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}   (lane (r, half) reads part of column r of L_{k+1})
-  if (warp == 0 && nb > 1) {
-    auto load_col = [&](double (&dst)[CPL], int k) {
-      const double* p = W.Lsub + size_t(k) * BS * ld + size_t(half * CPL) * ld + rr;
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) dst[i] = p[i * ld];
-    };
-    double La[CPL], Lb[CPL];
-    load_col(La, nb - 1);
-    for (int k = nb - 2; k >= 0; k -= 2) {
-      if (k > 0) load_col(Lb, k);
-      sweep_stage<BS>(La, bx + (k + 1) * BS + half * CPL, bx + k * BS + rr, writer);
-      if (k > 0) {
-        if (k > 1) load_col(La, k - 1);
-        sweep_stage<BS>(Lb, bx + k * BS + half * CPL, bx + (k - 1) * BS + rr, writer);
-      }
-    }
-  }
-  __syncthreads();
 }
 
 }  // namespace direct
