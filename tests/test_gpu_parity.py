@@ -347,3 +347,38 @@ def test_verbose_mode_and_gen_code(native, capfd):
     assert np.allclose(xq, xl, rtol=0, atol=1e-9)
     saved = Path(native.SHARE_DIR) / "code_gen" / "localSystemFunction.casadi"
     assert saved.exists() and saved.stat().st_size > 1000
+
+
+def _random_qp(seed, n, m_extra, density=0.3):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    M = rng.standard_normal((n, n)) * (rng.random((n, n)) < density)
+    P = M @ M.T + n * np.eye(n)
+    G = rng.standard_normal((m_extra, n)) * (rng.random((m_extra, n)) < density)
+    A = np.vstack([np.eye(n), G])
+    xf = rng.standard_normal(n)
+    l = np.concatenate([xf - rng.random(n), G @ xf - rng.random(m_extra)])
+    u = np.concatenate([xf + rng.random(n), G @ xf + rng.random(m_extra)])
+    l[n:n + 2] = u[n:n + 2] = (G @ xf)[:2]
+    q = rng.standard_normal(n)
+
+    def csc(Mat):
+        S = sp.csc_matrix(Mat); S.sort_indices()
+        return S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data.astype(np.float64)
+    return csc(P), q, csc(A), l, u
+
+
+@pytest.mark.parametrize("n,m_extra", [(12, 9), (40, 25), (90, 40)])
+def test_cucaqp_class_on_general_patterns(native, n, m_extra):
+    """The CuCaQP life cycle (setDimension / setSystem / initSolver / solve / getSolution,
+    CuCaQP.cpp:22-41, 271-288, 183-224) on QPs without stage structure: a single dense block up to
+    64 columns (direct kernel), wider patterns through the PCG fallback kernel."""
+    (hp, hi, hx), q, (ap, ai, ax), l, u = _random_qp(1000 + n, n, m_extra)
+    m = n + m_extra
+    x, y, info = native.cucaqp_solve(n, m, hp, hi, hx, q, ap, ai, ax, l, u, eps_abs=1e-6, eps_rel=1e-6)
+    ox, oy, oinfo, _ = _oracle.qp_solve(n, m, hp, hi, hx, q, ap, ai, ax, l, u,
+                                        settings=_oracle.settings_vector(eps_abs=1e-6, eps_rel=1e-6))
+    assert info[native.INFO["status"]] == oinfo[0] == native.QP_SOLVED
+    assert info[native.INFO["iters"]] == oinfo[1]
+    assert rel_err(x, ox) < REL_SOLUTION
+    assert rel_err(y, oy) < REL_SOLUTION
