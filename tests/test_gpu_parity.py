@@ -382,3 +382,42 @@ def test_cucaqp_class_on_general_patterns(native, n, m_extra):
     assert info[native.INFO["iters"]] == oinfo[1]
     assert rel_err(x, ox) < REL_SOLUTION
     assert rel_err(y, oy) < REL_SOLUTION
+
+
+def test_inconsistent_bounds_give_a_zero_step(problems, native):
+    """lbx > ubx on one variable: osqp_setup rejects the QP (validate_data); the reference ignores
+    the failure (SQPOptimizationSolver.cpp:155-157) -- restated as a zero step on both sides."""
+    prob, ora = problems("quadrotor")
+    frames, refs = prob.sample_inputs(3, 17)
+    lbx, ubx = prob.lbx.copy(), prob.ubx.copy()
+    lbx[40], ubx[40] = 1.0, -1.0
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = 0.5, 2
+    prob.solver.update_settings(s)
+    x0 = np.tile(frames, (1, prob.horizon))
+    x = x0.copy(); st = np.zeros((3, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, lbx, ubx, prob.lbg, prob.ubg, x, None, st)
+    assert np.array_equal(x, x0)
+    assert (st[:, native.STAT["qp_status"]] == native.QP_UNSOLVED).all()
+    assert (st[:, native.STAT["admm_iters"]] == 0).all()
+
+
+def test_adaptive_rho_inside_a_batched_solve(problems, native):
+    """Tight tolerances force rho updates (refactorisations on the device) inside the throughput plan."""
+    prob, ora = problems("quadrotor")
+    B = 160
+    frames, refs = prob.sample_inputs(B, 23)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = 1.0, 2
+    s.eps_abs = s.eps_rel = 1e-7
+    prob.solver.update_settings(s)
+    x = np.zeros((B, prob.N)); st = np.zeros((B, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, None, st)
+    assert (st[:, native.STAT["rho_updates"]] >= 1).sum() > B // 4     # a good part of the batch adapts rho
+    pick = [0, 79, 159] + [int(b) for b in np.flatnonzero(st[:, native.STAT["rho_updates"]] >= 1)[:3]]
+    ora.set_schedule(2, 1.0)
+    ora.set_qp_settings(_oracle.settings_from_b200(s))
+    ox, of, ost = ora.solve_batch(frames[pick], refs[pick])
+    assert np.array_equal(st[pick][:, native.STAT["admm_iters"]], ost[:, 2])
+    assert np.array_equal(st[pick][:, native.STAT["rho_updates"]], ost[:, 7])
+    assert rel_err(x[pick], ox) < REL_SOLUTION
