@@ -421,3 +421,25 @@ def test_adaptive_rho_inside_a_batched_solve(problems, native):
     assert np.array_equal(st[pick][:, native.STAT["admm_iters"]], ost[:, 2])
     assert np.array_equal(st[pick][:, native.STAT["rho_updates"]], ost[:, 7])
     assert rel_err(x[pick], ox) < REL_SOLUTION
+
+
+@pytest.mark.parametrize("max_iter,eps", [(60, 1e-12), (40, 2e-5), (25, 1e-12)])
+def test_iteration_limit_statuses(problems, native, max_iter, eps):
+    """max_iter reached: OSQP re-tests with 10x tolerances (SOLVED_INACCURATE) before reporting
+    MAX_ITER_REACHED; the last iterate is returned either way.  Also covers limits that are not a
+    multiple of check_termination."""
+    prob, ora = problems("quadrotor")
+    hv, q, av, l, u = _qp_case(prob, ora, 31, B=2)
+    s = prob.get_settings()
+    s.eps_abs = s.eps_rel = eps
+    s.admm_max_iter = max_iter
+    prob.solver.update_settings(s)
+    x, y, info = prob.solver.qp_solve_batch(hv, q, av, l, u)
+    sv = _oracle.settings_from_b200(s)
+    for b in range(2):
+        ox, oy, oinfo, _ = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[b], q[b], prob.a_colptr,
+                                            prob.a_rowidx, av[b], l[b], u[b], settings=sv)
+        assert info[b, native.INFO["status"]] == oinfo[0]
+        assert oinfo[0] in (native.QP_MAX_ITER, native.QP_SOLVED_INACCURATE, native.QP_SOLVED)
+        assert info[b, native.INFO["iters"]] == oinfo[1] <= max_iter
+        assert rel_err(x[b], ox) < REL_SOLUTION
