@@ -191,7 +191,8 @@ int ocp_b200_admm_trace(ocp_b200_solver* s, const double* h_vals, const double* 
 long long ocp_b200_launch_count(const ocp_b200_solver* s);
 /* Optional per-kernel device timing for bench.py's roofline: when enabled, every kernel launch
  * of this handle is bracketed by a CUDA event pair on the launching stream.  get_profile waits
- * for the recorded events and returns accumulated milliseconds and launch counts per kind. */
+ * for the recorded events and returns accumulated milliseconds and launch counts per kind.
+ * enabled = 1: event pairs only; 2: additionally the per-phase cycle counters below. */
 #define OCP_B200_NPROF 3
 #define OCP_B200_PROF_ADMM      0  /* admm_solve_kernel (one launch per SQP step)   */
 #define OCP_B200_PROF_ASSEMBLE  1  /* stage-library assembly kernel                 */

@@ -248,8 +248,9 @@ class Solver:
     def launch_count(self) -> int:
         return int(cuda_lib().ocp_b200_launch_count(self._h))
 
-    def set_profiling(self, enabled: bool) -> None:
-        _check(cuda_lib().ocp_b200_set_profiling(self._h, int(enabled)))
+    def set_profiling(self, enabled, phases: bool = False) -> None:
+        """enabled: CUDA-event pairs around every launch; phases: also the per-phase cycle counters of CTA 0."""
+        _check(cuda_lib().ocp_b200_set_profiling(self._h, 2 if (enabled and phases) else int(bool(enabled))))
 
     def get_profile(self, reset: bool = True) -> dict:
         """Accumulated device milliseconds / launch counts per kernel kind since the last reset."""

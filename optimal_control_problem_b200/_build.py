@@ -91,7 +91,8 @@ def compile_objects(sources: list[str], flags: list[str], objdir: Path, tag: str
 
 
 CUDA_SOURCES = ["csrc/ocp_b200.cu", "csrc/direct_smem.cu", "csrc/direct_mixed.cu", "csrc/direct_multi.cu"]
-NVCC_FLAGS = [*ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + str(INCLUDE), "-I" + str(PKG / "csrc")]
+NVCC_FLAGS = [*ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + str(INCLUDE), "-I" + str(PKG / "csrc"),
+              *os.environ.get("OCP_B200_NVCC_EXTRA", "").split()]
 
 
 def build_cuda(force: bool = False) -> Path:

@@ -186,6 +186,16 @@ struct PhaseClock {
   }
 };
 
+// The finer split of the solve / factor phases costs a predicated branch per lap in every thread;
+// it is compiled in only with -DOCP_B200_FINE_PHASES (tools/phase_profile.py documents the numbers).
+#ifdef OCP_B200_FINE_PHASES
+#define OCP_B200_FINE_CLOCK(name, ptr) PhaseClock name(ptr)
+#define OCP_B200_FINE_LAP(name, phase) name.lap(phase)
+#else
+#define OCP_B200_FINE_CLOCK(name, ptr)
+#define OCP_B200_FINE_LAP(name, phase)
+#endif
+
 struct QpResult {
   int status, iters, pcg_iters, rho_updates, checks;
   double prim_res, dual_res, rho;

@@ -404,11 +404,11 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int np = P.tri_np, bs = P.tri_bs, nb = P.tri_nb, ld = P.tri_ld, N = nb * bs;
   double* bx = W.b + np;
-  PhaseClock clk(W.phase);
+  OCP_B200_FINE_CLOCK(clk, W.phase);
   // forward sweep: y_k = b_k - L_k y_{k-1}
   coop_sweep<false>(P, W, bx);
   __syncthreads();
-  clk.lap(OCP_B200_PHASE_SOLVE_FWD);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
   // border: y_p = b_p - sum_k L_pk y_k  (a warp per border row), x_p = D_p^-1 y_p
   if (np > 0) {
     for (int r = warp; r < np; r += nw) {
@@ -428,7 +428,7 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
     }
     __syncthreads();
   }
-  clk.lap(OCP_B200_PHASE_SOLVE_BORDER);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
   // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
   const int Tb = (T / bs) * bs;   // whole blocks per pass: a pass never reads what it overwrites
   for (int base = 0; base < N; base += Tb) {
@@ -451,11 +451,11 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
     if (j < N) bx[j] = v;
   }
   __syncthreads();
-  clk.lap(OCP_B200_PHASE_SOLVE_DIAG);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
   // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}
   coop_sweep<true>(P, W, bx);
   __syncthreads();
-  clk.lap(OCP_B200_PHASE_SOLVE_BWD);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
 }
 
 }  // namespace direct

@@ -457,7 +457,7 @@ int launch_admm(ocp_b200_solver* s, SolveArgs& A, cudaStream_t st) {
   CUDA_TRY(s->counter.reserve(1));
   CUDA_TRY(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
   A.counter = s->counter.p;
-  A.phase = s->profiling ? s->phase.p : nullptr;
+  A.phase = s->profiling >= 2 ? s->phase.p : nullptr;
   int grid = std::min(A.B, s->max_ctas);
   ProfScope prof(s, OCP_B200_PROF_ADMM, st);
   if (s->use_direct) {
@@ -793,8 +793,8 @@ long long ocp_b200_launch_count(const ocp_b200_solver* s) { return s ? s->launch
 
 int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled) {
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
-  s->profiling = enabled ? 1 : 0;
-  if (enabled) {
+  s->profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
+  if (enabled >= 2) {
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(s->phase.reserve(OCP_B200_NPHASE));
     CUDA_TRY(cudaMemset(s->phase.p, 0, OCP_B200_NPHASE * sizeof(long long)));

@@ -83,13 +83,13 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   for (int e = gt; e < np * (np + 1); e += GT) Dpacc[e] = 0.0;
   // both chains: invert the chain's current block, then eliminate into the next one
   if (grp == 0) {
-    PhaseClock clk(W.phase);
+    OCP_B200_FINE_CLOCK(clk, W.phase);
     for (int k = 0; k < mid; ++k) {           // blocks 0..mid-1; step into k+1 (the last one is mid)
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(1, GT);
-      clk.lap(OCP_B200_PHASE_FACTOR_INVERT);
+      OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_INVERT);
       chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1);
-      clk.lap(OCP_B200_PHASE_FACTOR_STEP);
+      OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_STEP);
     }
   } else {
     for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
@@ -182,7 +182,7 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   constexpr int ld = BS + 2;
   const int mid = nb / 2;
   double* bx = W.b + np;
-  PhaseClock clk(W.phase);
+  OCP_B200_FINE_CLOCK(clk, W.phase);
   // forward: top chain y_k = b_k - L_k y_{k-1} (k = 1..mid-1) and bottom chain
   // y_k = b_k - U_k y_{k+1} (k = nb-2..mid+1) on two warps, then both contributions to block mid
   if (warp == 0) run_chain<BS, false>(W, bx, ld, 1, 1, 1, 0, 1, mid - 1, lane);
@@ -193,7 +193,7 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
     if (mid + 1 < nb) run_chain<BS, false>(W, bx, ld, mid + 1, 1, mid, mid + 1, 1, 1, lane);
   }
   __syncthreads();
-  clk.lap(OCP_B200_PHASE_SOLVE_FWD);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
   // border: y_p = b_p - sum_k L_pk y_k  (half a warp per border row, loads issued in batches of 8
   // so that a slab-resident L_p costs one L2 latency per batch), x_p = D_p^-1 y_p
   if (np > 0) {
@@ -233,7 +233,7 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
     }
     __syncthreads();
   }
-  clk.lap(OCP_B200_PHASE_SOLVE_BORDER);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
   // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
   {
     const int Tb = (T / BS) * BS;   // whole blocks per pass: a pass never reads what it overwrites
@@ -244,12 +244,20 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
       if (j < N) {
         v = dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
         double v1 = 0.0;
-        int p = 0;
-        for (; p + 1 < np; p += 2) {
-          v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
-          v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
+        if (np == 12) {   // the border size of a 12-state reference: all loads issued before the first FMA
+          double lv[12];
+#pragma unroll
+          for (int p = 0; p < 12; ++p) lv[p] = W.Lp[size_t(p) * N + j];
+#pragma unroll
+          for (int p = 0; p < 12; p += 2) { v = fma(-lv[p], W.b[p], v); v1 = fma(-lv[p + 1], W.b[p + 1], v1); }
+        } else {
+          int p = 0;
+          for (; p + 1 < np; p += 2) {
+            v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+            v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
+          }
+          if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
         }
-        if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
         v += v1;
       }
       __syncthreads();
@@ -257,13 +265,13 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
     }
   }
   __syncthreads();
-  clk.lap(OCP_B200_PHASE_SOLVE_DIAG);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
   // backward, from block mid outwards: x_k = c_k - L_{k+1}' x_{k+1} (k = mid-1..0) and
   // x_k = c_k - U_{k-1}' x_{k-1} (k = mid+1..nb-1)
   if (warp == 0) run_chain<BS, true>(W, bx, ld, mid, -1, mid - 1, mid, -1, mid, lane);
   else if (warp == 1) run_chain<BS, true>(W, bx, ld, mid + 1, 1, mid + 1, mid, 1, nb - 1 - mid, lane);
   __syncthreads();
-  clk.lap(OCP_B200_PHASE_SOLVE_BWD);
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
 }
 
 }  // namespace direct

@@ -1,4 +1,6 @@
 """Per-phase SM-cycle breakdown of the direct ADMM kernel (CTA 0), for DESIGN.md / profiles/.
+The solve_* / factor_* sub-phases are only counted when libocp_b200.so is built with -DOCP_B200_FINE_PHASES
+(OCP_B200_NVCC_EXTRA="-DOCP_B200_FINE_PHASES" python -c "from optimal_control_problem_b200 import _build; _build.build_cuda(force=True)").
 usage: python tools/phase_profile.py [problem] [B]"""
 import sys
 import time
@@ -16,7 +18,7 @@ frames, refs = prob.sample_inputs(B, 1)
 sol = prob.solver
 x = np.zeros((B, prob.N)); st = np.zeros((B, ocp.NSTATS))
 sol.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, None, st)
-sol.set_profiling(True)
+sol.set_profiling(True, phases=True)
 x[:] = 0
 t = time.time()
 sol.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, None, st)
