@@ -41,7 +41,9 @@ namespace direct {
 //   PLACE_MULTI  vectors, A values and small scratch in shared memory, factor blocks / index
 //                arrays / rarely used vectors in global memory (L2-resident): ~65 KB per CTA, so that
 //                three CTAs share an SM and hide each other's dependent-latency chains
-enum Placement { PLACE_MIXED = 0, PLACE_SMEM = 1, PLACE_MULTI = 2 };
+//   PLACE_BIG    one CTA per SM for problems whose factor does not fit: vectors, A values, scratch and
+//                index arrays in shared memory, factor blocks and set-up / check vectors in global memory
+enum Placement { PLACE_MIXED = 0, PLACE_SMEM = 1, PLACE_MULTI = 2, PLACE_BIG = 3 };
 
 // arrays of the per-instance state, in shared-memory priority order
 enum ArrayId {
@@ -51,6 +53,7 @@ enum ArrayId {
 // throughput plan: vectors, A values, scratch, index arrays + the small set-up / check vectors in
 // shared memory (107 KB for the quadrotor, two CTAs per SM); the factor blocks in the global slab
 __host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX || id == AR_PVAL || id >= AR_D; }
+__host__ __device__ constexpr bool big_in_smem(int id) { return id <= AR_IDX; }
 
 struct Work {
   double *x, *q, *b, *z, *y, *l, *u;
@@ -90,7 +93,7 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
 #pragma unroll
   for (int id = 0; id < AR_COUNT; ++id) {
     const size_t sz = (array_doubles(P, id) + 1) & ~size_t(1);
-    const bool in_smem = kPlace == PLACE_SMEM ? true : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (smem_mask >> id & 1u) != 0);
+    const bool in_smem = kPlace == PLACE_SMEM ? true : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (kPlace == PLACE_BIG ? big_in_smem(id) : (smem_mask >> id & 1u) != 0));
     if (in_smem) { ptr[id] = sm; sm += sz; }
     else { ptr[id] = gl; gl += sz; }
   }

@@ -9,7 +9,7 @@ namespace direct {
 
 struct KernelInfo { int static_smem; int regs; int threads; };
 
-// place: 0 = mixed placement (run-time mask), 1 = all shared memory, 2 = multi-CTA-per-SM split
+// place: 0 = mixed placement (run-time mask), 1 = all shared memory, 2 = multi-CTA-per-SM split, 3 = big problems
 cudaError_t kernel_info(int place, KernelInfo* out);
 cudaError_t set_max_dynamic_smem(int place, int bytes);
 cudaError_t occupancy(int place, int dyn_smem, int* per_sm);
@@ -20,6 +20,7 @@ cudaError_t launch(int place, int grid, int dyn_smem, cudaStream_t st, const Pat
 size_t plan_array_doubles(const PatternDev& P, int id);
 int plan_array_count();
 bool plan_multi_in_smem(int id);
+bool plan_big_in_smem(int id);
 
 }  // namespace direct
 }  // namespace ocpb200

@@ -33,28 +33,34 @@ cudaError_t launch_smem(int grid, int dyn_smem, cudaStream_t st, const PatternDe
                            const SolveArgs& A, uint32_t smem_mask);
 DECL(mixed)
 DECL(multi)
+DECL(big)
 #undef DECL
 
 size_t plan_array_doubles(const PatternDev& P, int id) { return array_doubles(P, id); }
 int plan_array_count() { return AR_COUNT; }
 bool plan_multi_in_smem(int id) { return multi_in_smem(id); }
+bool plan_big_in_smem(int id) { return big_in_smem(id); }
 
 cudaError_t kernel_info(int place, KernelInfo* out) {
-  return place == PLACE_SMEM ? kernel_info_smem(out) : (place == PLACE_MULTI ? kernel_info_multi(out) : kernel_info_mixed(out));
+  return place == PLACE_SMEM ? kernel_info_smem(out)
+                             : (place == PLACE_MULTI ? kernel_info_multi(out) : (place == PLACE_BIG ? kernel_info_big(out) : kernel_info_mixed(out)));
 }
 cudaError_t set_max_dynamic_smem(int place, int bytes) {
   return place == PLACE_SMEM ? set_max_dynamic_smem_smem(bytes)
-                             : (place == PLACE_MULTI ? set_max_dynamic_smem_multi(bytes) : set_max_dynamic_smem_mixed(bytes));
+                             : (place == PLACE_MULTI ? set_max_dynamic_smem_multi(bytes)
+                                                     : (place == PLACE_BIG ? set_max_dynamic_smem_big(bytes) : set_max_dynamic_smem_mixed(bytes)));
 }
 cudaError_t occupancy(int place, int dyn_smem, int* per_sm) {
   return place == PLACE_SMEM ? occupancy_smem(dyn_smem, per_sm)
-                             : (place == PLACE_MULTI ? occupancy_multi(dyn_smem, per_sm) : occupancy_mixed(dyn_smem, per_sm));
+                             : (place == PLACE_MULTI ? occupancy_multi(dyn_smem, per_sm)
+                                                     : (place == PLACE_BIG ? occupancy_big(dyn_smem, per_sm) : occupancy_mixed(dyn_smem, per_sm)));
 }
 cudaError_t launch(int place, int grid, int dyn_smem, cudaStream_t st, const PatternDev& P, const ocp_b200_settings& S,
                    const SolveArgs& A, uint32_t smem_mask) {
   return place == PLACE_SMEM ? launch_smem(grid, dyn_smem, st, P, S, A, smem_mask)
                              : (place == PLACE_MULTI ? launch_multi(grid, dyn_smem, st, P, S, A, smem_mask)
-                                                     : launch_mixed(grid, dyn_smem, st, P, S, A, smem_mask));
+                                                     : (place == PLACE_BIG ? launch_big(grid, dyn_smem, st, P, S, A, smem_mask)
+                                                                           : launch_mixed(grid, dyn_smem, st, P, S, A, smem_mask)));
 }
 
 }  // namespace direct

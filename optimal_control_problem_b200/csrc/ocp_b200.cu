@@ -333,11 +333,12 @@ int plan_launch(ocp_b200_solver* s) {
     // memory (everything, for the H=20 quadrotor) -- the latency plan, used for small batches.
     // OCP_B200_PLAN = smem | multi | mixed forces one of them (diagnostics).
     const char* env = std::getenv("OCP_B200_PLAN");
-    size_t multi_smem = 0, multi_slab = 0, all = 0;
+    size_t multi_smem = 0, multi_slab = 0, big_smem = 0, big_slab = 0, all = 0;
     for (int id = 0; id < count; ++id) {
       const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
       all += sz;
       (D::plan_multi_in_smem(id) ? multi_smem : multi_slab) += sz;
+      (D::plan_big_in_smem(id) ? big_smem : big_slab) += sz;
     }
     auto make_plan = [&](int place, LaunchPlan& L) -> int {
       D::KernelInfo kx{};
@@ -349,6 +350,10 @@ int plan_launch(ocp_b200_solver* s) {
         L.smem_mask = 0;
         L.smem_bytes = static_cast<int>(multi_smem * sizeof(double));
         L.slab_doubles = (multi_slab + 15) & ~size_t(15);
+      } else if (place == 3) {
+        L.smem_mask = 0;
+        L.smem_bytes = static_cast<int>(big_smem * sizeof(double));
+        L.slab_doubles = (big_slab + 15) & ~size_t(15);
       } else {
         size_t avail = (size_t(max_optin) - kx.static_smem) / sizeof(double), used = 0, slab = 0;
         uint32_t mask = 0;
@@ -371,10 +376,14 @@ int plan_launch(ocp_b200_solver* s) {
     CUDA_TRY(D::kernel_info(2, &km));
     const bool fits_all = all * sizeof(double) + ki.static_smem <= size_t(max_optin);
     const bool fits_multi = (multi_smem * sizeof(double) + km.static_smem + 1024) * 2 <= size_t(228) * 1024;
-    int deep = fits_all ? 1 : 0, wide = fits_multi ? 2 : deep;
+    D::KernelInfo kb{};
+    CUDA_TRY(D::kernel_info(3, &kb));
+    const bool fits_big = big_smem * sizeof(double) + kb.static_smem <= size_t(max_optin);
+    int deep = fits_all ? 1 : (fits_big ? 3 : 0), wide = fits_multi ? 2 : deep;
     if (env && !std::strcmp(env, "multi") && fits_multi) deep = wide = 2;
     else if (env && !std::strcmp(env, "mixed")) deep = wide = 0;
     else if (env && !std::strcmp(env, "smem") && fits_all) deep = wide = 1;
+    else if (env && !std::strcmp(env, "big") && fits_big) deep = wide = 3;
     RC_TRY(make_plan(deep, s->deep));
     RC_TRY(make_plan(wide, s->wide));
     s->place = s->wide.place; s->threads = s->wide.threads; s->smem_bytes = s->wide.smem_bytes;
