@@ -47,12 +47,15 @@ enum Placement { PLACE_MIXED = 0, PLACE_SMEM = 1, PLACE_MULTI = 2, PLACE_BIG = 3
 
 // arrays of the per-instance state, in shared-memory priority order
 enum ArrayId {
-  AR_X = 0, AR_Q, AR_B, AR_Z, AR_Y, AR_L, AR_U, AR_CTYPE, AR_W, AR_AVAL, AR_SCRATCH, AR_IDX, AR_DINV, AR_LSUB, AR_PVAL,
-  AR_LP, AR_D, AR_E, AR_DX, AR_DY, AR_COUNT
+  AR_X = 0, AR_Q, AR_B, AR_Z, AR_Y, AR_L, AR_U, AR_CTYPE, AR_W, AR_AVAL, AR_SCRATCH, AR_STAGE, AR_IDX, AR_DINV, AR_LSUB,
+  AR_PVAL, AR_LP, AR_D, AR_E, AR_DX, AR_DY, AR_COUNT
 };
-// throughput plan: vectors, A values, scratch, index arrays + the small set-up / check vectors in
-// shared memory (107 KB for the quadrotor, two CTAs per SM); the factor blocks in the global slab
-__host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX || id == AR_PVAL || id >= AR_D; }
+// AR_STAGE: two pairs of block buffers in which the factorisation stages the blocks it multiplies
+// when the factor itself lives in the global slab; not allocated when everything is in shared memory.
+// throughput plan: vectors, A values, scratch, block staging buffers, index arrays + the small set-up /
+// scaling vectors in shared memory (109 KB for the quadrotor, two CTAs per SM); the factor blocks and
+// dx, dy (read at termination checks only) in the global slab
+__host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX || id == AR_PVAL || id == AR_D || id == AR_E; }
 __host__ __device__ constexpr bool big_in_smem(int id) { return id <= AR_IDX; }
 
 struct Work {
@@ -61,6 +64,8 @@ struct Work {
   double *Aval, *Dinv, *Lsub;
   idx_t* idx;
   double *Pval;
+  double *stage;   // block staging buffers (null when the factor is in shared memory anyway)
+  int stage_stride;
   double *Lp, *Dp, *Dp2, *S, *Sp, *xp, *piv;   // border: L_pk [np x N], D_p^-1 [np x (np+1)], scratch (two sets)
   int s_stride, sp_stride;
   long long* phase;   // cycle counters of CTA 0 (null unless profiling)
@@ -78,6 +83,7 @@ __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
     case AR_PVAL: return (size_t(P.nnz_p) + 1) & ~size_t(1);
     case AR_DINV: case AR_LSUB: return nb * bs * ld;
     case AR_IDX: return (size_t(P.idx_entries) * sizeof(idx_t) + 7) / 8;
+    case AR_STAGE: return 4 * ((bs * ld + 1) & ~size_t(1));
     case AR_LP: return (np * nb * bs + 1) & ~size_t(1);
     case AR_SCRATCH: return 3 * np * (np + 1) + 2 * ((bs * ld + 1) & ~size_t(1)) + 2 * ((np * bs + 1) & ~size_t(1)) +
                             ((np + 2) & ~size_t(1)) + 64;
@@ -92,7 +98,7 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
   double* ptr[AR_COUNT];
 #pragma unroll
   for (int id = 0; id < AR_COUNT; ++id) {
-    const size_t sz = (array_doubles(P, id) + 1) & ~size_t(1);
+    const size_t sz = (kPlace == PLACE_SMEM && id == AR_STAGE) ? 0 : ((array_doubles(P, id) + 1) & ~size_t(1));
     const bool in_smem = kPlace == PLACE_SMEM ? true : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (kPlace == PLACE_BIG ? big_in_smem(id) : (smem_mask >> id & 1u) != 0));
     if (in_smem) { ptr[id] = sm; sm += sz; }
     else { ptr[id] = gl; gl += sz; }
@@ -104,6 +110,8 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
   W.Pval = ptr[AR_PVAL];
   const size_t np = P.tri_np;
   W.Lp = ptr[AR_LP];
+  W.stage = kPlace == PLACE_SMEM ? nullptr : ptr[AR_STAGE];
+  W.stage_stride = static_cast<int>((size_t(P.tri_bs) * P.tri_ld + 1) & ~size_t(1));
   double* bp = ptr[AR_SCRATCH];
   W.Dp = bp; bp += np * (np + 1);
   W.Dp2 = bp; bp += 2 * np * (np + 1);

@@ -21,6 +21,7 @@ size_t plan_array_doubles(const PatternDev& P, int id);
 int plan_array_count();
 bool plan_multi_in_smem(int id);
 bool plan_big_in_smem(int id);
+int plan_stage_array();
 
 }  // namespace direct
 }  // namespace ocpb200

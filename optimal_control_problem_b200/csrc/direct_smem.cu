@@ -40,6 +40,7 @@ size_t plan_array_doubles(const PatternDev& P, int id) { return array_doubles(P,
 int plan_array_count() { return AR_COUNT; }
 bool plan_multi_in_smem(int id) { return multi_in_smem(id); }
 bool plan_big_in_smem(int id) { return big_in_smem(id); }
+int plan_stage_array() { return AR_STAGE; }
 
 cudaError_t kernel_info(int place, KernelInfo* out) {
   return place == PLACE_SMEM ? kernel_info_smem(out)

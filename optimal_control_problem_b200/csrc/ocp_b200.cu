@@ -334,9 +334,10 @@ int plan_launch(ocp_b200_solver* s) {
     // OCP_B200_PLAN = smem | multi | mixed forces one of them (diagnostics).
     const char* env = std::getenv("OCP_B200_PLAN");
     size_t multi_smem = 0, multi_slab = 0, big_smem = 0, big_slab = 0, all = 0;
+    const int stage_id = D::plan_stage_array();   // not allocated by the all-shared-memory plan
     for (int id = 0; id < count; ++id) {
       const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
-      all += sz;
+      if (id != stage_id) all += sz;
       (D::plan_multi_in_smem(id) ? multi_smem : multi_slab) += sz;
       (D::plan_big_in_smem(id) ? big_smem : big_slab) += sz;
     }
@@ -358,7 +359,7 @@ int plan_launch(ocp_b200_solver* s) {
         size_t avail = (size_t(max_optin) - kx.static_smem) / sizeof(double), used = 0, slab = 0;
         uint32_t mask = 0;
         for (int id = 0; id < count; ++id) {
-          const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
+          const size_t sz = (place == 1 && id == stage_id) ? 0 : ((D::plan_array_doubles(P, id) + 1) & ~size_t(1));
           if (place == 1 || used + sz <= avail) { mask |= 1u << id; used += sz; }
           else slab += sz;
         }

@@ -27,12 +27,25 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 // Updates D_k (not inverted here), V_k, finalises L_p,pred, accumulates into Dpacc, overwrites the slot.
 template <int BS, bool kTop>
 __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*ld*/, int k, int pred, int slot, double* S,
-                                           double* Sp, double* Dpacc, int gt, int GT, int bar) {
+                                           double* Sp, double* Dpacc, int gt, int GT, int bar, double* stage) {
   constexpr int bb = BS * BS, ld = BS + 2;   // compile-time pitch: addresses fold into immediates
   const int pb = np * BS;
-  double* C = W.Lsub + size_t(slot) * BS * ld;
+  double* Cg = W.Lsub + size_t(slot) * BS * ld;
   double* Dk = W.Dinv + size_t(k) * BS * ld;
-  const double* Dm = W.Dinv + size_t(pred) * BS * ld;   // D_pred^-1 (symmetric)
+  const double* Dg = W.Dinv + size_t(pred) * BS * ld;   // D_pred^-1 (symmetric)
+  // With the factor in the global slab every dot product below would re-read block rows from L2:
+  // copy the two blocks this step multiplies into shared memory once (coalesced 16-byte loads).
+  const double* C = Cg;
+  const double* Dm = Dg;
+  if (stage != nullptr) {
+    double2* cs = reinterpret_cast<double2*>(stage);
+    double2* ds = reinterpret_cast<double2*>(stage + W.stage_stride);
+    const double2* cg2 = reinterpret_cast<const double2*>(Cg);
+    const double2* dg2 = reinterpret_cast<const double2*>(Dg);
+    for (int e = gt; e < BS * ld / 2; e += GT) { cs[e] = cg2[e]; ds[e] = dg2[e]; }
+    group_barrier(bar, GT);
+    C = stage; Dm = stage + W.stage_stride;
+  }
   // coupling block into S; V_pred into Sp
   for (int e = gt; e < bb; e += GT) {
     const int r = e / BS, c = e % BS;
@@ -63,7 +76,7 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
   }
   for (int e = gt; e < bb; e += GT) {
     const int r = e / BS, c = e % BS;
-    C[r * ld + c] = S[r * ld + c];
+    Cg[r * ld + c] = S[r * ld + c];
   }
   group_barrier(bar, GT);
 }
@@ -80,6 +93,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   double* Sp = W.Sp + grp * W.sp_stride;
   double* piv = W.piv + grp * 32;
   double* Dpacc = W.Dp2 + grp * np * (np + 1);
+  double* stage = W.stage ? W.stage + grp * 2 * W.stage_stride : nullptr;
   for (int e = gt; e < np * (np + 1); e += GT) Dpacc[e] = 0.0;
   // both chains: invert the chain's current block, then eliminate into the next one
   if (grp == 0) {
@@ -88,14 +102,14 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(1, GT);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_INVERT);
-      chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1);
+      chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_STEP);
     }
   } else {
     for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(2, GT);
-      chain_step<BS, false>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2);
+      chain_step<BS, false>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage);
     }
     if (mid + 1 < nb) {                       // block mid+1: inverted here, eliminated into mid below
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid + 1) * BS * ld, ld, lane, piv);
@@ -104,7 +118,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   }
   __syncthreads();
   // the bottom chain's last step lands on block mid as well: run it with the whole CTA
-  if (mid + 1 < nb) chain_step<BS, false>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0);
+  if (mid + 1 < nb) chain_step<BS, false>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage);
   if (tid < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid) * BS * ld, ld, lane, W.piv);
   __syncthreads();
   // border of the last block, then D_p = K_pp - (accumulated) - V_mid L_p,mid', inverted
