@@ -526,15 +526,23 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
   }
 
   clk.lap(OCP_B200_PHASE_LOAD);
-  // ---- Ruiz equilibration (scale_data): D, E, c;  scratch: b (n), dy (m) ---------------------
+  // ---- Ruiz equilibration (scale_data): D, E, c;  scratch: b (n), dy (m), x (n), w (n) --------
+  // The column norms of pass k+1 are by-products of the scaling of pass k: the scaled A column is in
+  // hand when it is written (x keeps its inf-norm), and the P column norm is the one computed for the
+  // cost normalisation times the cost factor ct (rounding is monotone, so the maximum commutes with
+  // the multiplication bit for bit).  Only the first pass reads the matrices for its column norms.
   double c = 1.0;
   for (int pass = 0; pass < S.scaling_iters; ++pass) {
     for (int j = tid; j < n; j += T) {
       double dn = 0.0;
+      if (pass == 0) {
 #pragma unroll 4
-      for (int k = P.p_colptr[j]; k < P.p_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Pval[k]));
+        for (int k = P.p_colptr[j]; k < P.p_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Pval[k]));
 #pragma unroll 4
-      for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Aval[k]));
+        for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) dn = fmax(dn, fabs(W.Aval[k]));
+      } else {
+        dn = fmax(W.w[j], W.x[j]);
+      }
       W.b[j] = 1.0 / sqrt(limit_scaling(dn));
     }
     for (int i = tid; i < m; i += T) {
@@ -547,14 +555,20 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
     double red[2] = {0.0, 0.0};  // sum of P column norms, max |q|
     for (int j = tid; j < n; j += T) {
       const double dj = W.b[j];
-      double cn = 0.0;
+      double cn = 0.0, an = 0.0;
       for (int k = P.p_colptr[j]; k < P.p_colptr[j + 1]; ++k) {
         const double v = W.Pval[k] * W.b[P.p_rowidx[k]] * dj;
         W.Pval[k] = v;
         cn = fmax(cn, fabs(v));
       }
 #pragma unroll 4
-      for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) W.Aval[k] *= W.dy[P.a_rowidx[k]] * dj;
+      for (int k = P.a_colptr[j]; k < P.a_colptr[j + 1]; ++k) {
+        const double v = W.Aval[k] * (W.dy[P.a_rowidx[k]] * dj);
+        W.Aval[k] = v;
+        an = fmax(an, fabs(v));
+      }
+      W.x[j] = an;      // inf-norm of the scaled A column
+      W.w[j] = cn;      // inf-norm of the scaled P column, before the cost factor
       const double qj = W.q[j] * dj;
       W.q[j] = qj;
       W.D[j] *= dj;
@@ -567,10 +581,11 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
     block_reduce<1, true>(mx, R);
     const double ct = 1.0 / limit_scaling(fmax(sum[0] / double(n), limit_scaling(mx[0])));
     for (int k = tid; k < P.nnz_p; k += T) W.Pval[k] *= ct;
-    for (int j = tid; j < n; j += T) W.q[j] *= ct;
+    for (int j = tid; j < n; j += T) { W.q[j] *= ct; W.w[j] *= ct; }
     c *= ct;
     __syncthreads();
   }
+  for (int j = tid; j < n; j += T) { W.x[j] = 0.0; W.w[j] = 0.0; }   // back to the cold start
   const double cinv = 1.0 / c;
 
   // ---- scaled bounds, constraint types (set_rho_vec) ------------------------------------------
