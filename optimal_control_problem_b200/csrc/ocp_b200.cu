@@ -188,7 +188,11 @@ int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
   // fall back to Jacobi for such partitions
   if (max_bs > 64) return fail(OCP_B200_ERR_UNSUPPORTED, "preconditioner blocks larger than 64 columns are not supported");
   std::vector<int> rows_long, rows_short;
-  for (int i = 0; i < m; ++i) (rowptr[i + 1] - rowptr[i] >= 8 ? rows_long : rows_short).push_back(i);
+  // rows with at least `long_row` entries are handled by four lanes each in the row-wise products,
+  // the others by one thread (OCP_B200_LONG_ROW overrides the threshold for experiments)
+  int long_row = 64;   // measured (quadrotor, rows of <= 17 entries): one thread per row beats four lanes per row by 7 %
+  if (const char* e = std::getenv("OCP_B200_LONG_ROW")) long_row = std::max(1, std::atoi(e));
+  for (int i = 0; i < m; ++i) (rowptr[i + 1] - rowptr[i] >= long_row ? rows_long : rows_short).push_back(i);
 
   if (n + 1 > 65535 || m + 1 > 65535 || s->nnz_a > 65535 || s->nnz_p > 65535)
     return fail(OCP_B200_ERR_UNSUPPORTED, "problem too large for 16-bit index structures (n, m, nnz < 65536)");
