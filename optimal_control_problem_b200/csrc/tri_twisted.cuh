@@ -197,6 +197,17 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   const int mid = nb / 2;
   double* bx = W.b + np;
   OCP_B200_FINE_CLOCK(clk, W.phase);
+  // The diagonal phase needs one row of D_k^-1 per thread; with the factor in the global slab that
+  // is an L2 round trip on the critical path.  The warps that idle during the forward sweep fetch
+  // their row now (first pass of the diagonal phase only) and keep it in registers.
+  const int dTb = (T / BS) * BS;
+  const bool pre = W.stage != nullptr && warp >= 2 && tid < dTb && tid < N;   // slab-resident factor only
+  double drow[BS];
+  if (pre) {
+    const double2* p2 = reinterpret_cast<const double2*>(W.Dinv + size_t(tid / BS) * BS * ld + (tid % BS) * ld);
+#pragma unroll
+    for (int i = 0; i < BS / 2; ++i) { const double2 v = p2[i]; drow[2 * i] = v.x; drow[2 * i + 1] = v.y; }
+  }
   // forward: top chain y_k = b_k - L_k y_{k-1} (k = 1..mid-1) and bottom chain
   // y_k = b_k - U_k y_{k+1} (k = nb-2..mid+1) on two warps, then both contributions to block mid
   if (warp == 0) run_chain<BS, false>(W, bx, ld, 1, 1, 1, 0, 1, mid - 1, lane);
@@ -256,7 +267,18 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
       const int j = tid < Tb ? base + tid : N;
       double v = 0.0;
       if (j < N) {
-        v = dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
+        if (pre && base == 0) {
+          const double* yk = bx + k * BS;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+          for (int t = 0; t < BS; t += 4) {
+            s0 = fma(drow[t], yk[t], s0); s1 = fma(drow[t + 1], yk[t + 1], s1);
+            s2 = fma(drow[t + 2], yk[t + 2], s2); s3 = fma(drow[t + 3], yk[t + 3], s3);
+          }
+          v = (s0 + s1) + (s2 + s3);
+        } else {
+          v = dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
+        }
         double v1 = 0.0;
         if (np == 12) {   // the border size of a 12-state reference: all loads issued before the first FMA
           double lv[12];
