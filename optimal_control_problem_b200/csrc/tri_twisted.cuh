@@ -175,6 +175,27 @@ __device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/,
       for (int i = 0; i < CPL; ++i) dst[i] = p[i * ld];
     }
   };
+  if (W.stage != nullptr && CPL <= 8) {
+    // slab-resident factor: three register buffers, block rows requested two stages ahead (an L2
+    // round trip under load is longer than one stage)
+    double La[CPL], Lb[CPL], Lc[CPL];
+    load(La, lp);
+    if (count > 1) load(Lb, lp + dl);
+    for (int i = 0; i < count; i += 3) {
+      if (i + 2 < count) load(Lc, lp + 2 * dl);
+      sweep_stage<BS>(La, srcp, dstp, writer);
+      if (i + 1 < count) {
+        if (i + 3 < count) load(La, lp + 3 * dl);
+        sweep_stage<BS>(Lb, srcp + db, dstp + db, writer);
+      }
+      if (i + 2 < count) {
+        if (i + 4 < count) load(Lb, lp + 4 * dl);
+        sweep_stage<BS>(Lc, srcp + 2 * db, dstp + 2 * db, writer);
+      }
+      lp += 3 * dl; srcp += 3 * db; dstp += 3 * db;
+    }
+    return;
+  }
   double La[CPL], Lb[CPL];
   load(La, lp);
   for (int i = 0; i < count; i += 2) {
