@@ -164,6 +164,13 @@ int ocp_b200_solve_batch_device(ocp_b200_solver* s, int B, const double* d_frame
                                 const double* d_ubg, double* d_x_inout, double* d_f_out, double* d_stats,
                                 void* stream);
 
+/* MPC tick loop.  The reference keeps its iterate across calls
+ * (result_["x"], SQPOptimizationSolver.cpp:215) exactly as the last solve left it; a
+ * receding-horizon caller shifts it by one stage before the next tick: frame k <- frame k+1
+ * for k < horizon-1, the last frame is repeated.  In place on d_x [B*N] (device pointer),
+ * asynchronous on `stream`. */
+int ocp_b200_shift_iterate_device(ocp_b200_solver* s, int B, double* d_x, void* stream);
+
 /* Parity hook for SQPOptimizationSolver::getLocalSystem (SQPOptimizationSolver.cpp:100-120):
  * evaluates the local system at x for B instances and returns it, values in CCS
  * order of the patterns given at create time.

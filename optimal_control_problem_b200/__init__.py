@@ -112,6 +112,7 @@ def cuda_lib() -> C.CDLL:
         lib.ocp_b200_get_settings.argtypes = [vptr, C.POINTER(Settings)]
         lib.ocp_b200_solve_batch.argtypes = [vptr, C.c_int] + [dptr] * 9
         lib.ocp_b200_solve_batch_device.argtypes = [vptr, C.c_int] + [vptr] * 9 + [vptr]
+        lib.ocp_b200_shift_iterate_device.argtypes = [vptr, C.c_int, vptr, vptr]
         lib.ocp_b200_export_qp.argtypes = [vptr, C.c_int] + [dptr] * 12
         lib.ocp_b200_qp_solve_batch.argtypes = [vptr, C.c_int] + [dptr] * 8
         lib.ocp_b200_admm_trace.argtypes = [vptr] + [dptr] * 5 + [C.c_int, dptr, C.POINTER(C.c_int), dptr, dptr]
@@ -150,6 +151,7 @@ def host_lib() -> C.CDLL:
         lib.ocp_host_compute_optimal_trajectory.argtypes = [vptr, dptr, dptr, dptr, dptr]
         lib.ocp_host_compute_optimal_trajectory_batch.argtypes = [vptr, C.c_int, dptr, dptr, dptr, dptr, dptr]
         lib.ocp_host_problem_reset.argtypes = [vptr]
+        lib.ocp_host_problem_shift_batch.argtypes = [vptr]
         lib.ocp_host_sample_inputs.argtypes = [C.c_char_p, C.c_int, C.c_ulonglong, dptr, dptr]
         lib.ocp_host_kat_create.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(vptr)]
         lib.ocp_host_kat_destroy.argtypes = [vptr]
@@ -289,6 +291,10 @@ class Solver:
         _check(cuda_lib().ocp_b200_solve_batch_device(self._h, B, d_frames, d_p, d_lbx, d_ubx, d_lbg, d_ubg, d_x,
                                                       d_f, d_stats, stream))
 
+    def shift_iterate_device(self, B, d_x, stream=0):
+        """ocp_b200_shift_iterate_device: frame k <- frame k+1 in place on the device iterate."""
+        _check(cuda_lib().ocp_b200_shift_iterate_device(self._h, B, d_x, stream))
+
     def export_qp(self, frames, p, lbx, ubx, lbg, ubg, x):
         """ocp_b200_export_qp: local system (H values, q, A values, l, u) of B instances."""
         x = _f64(x)
@@ -405,6 +411,73 @@ class Problem:
 
     def reset(self) -> None:
         _hcheck(host_lib().ocp_host_problem_reset(self._h))
+
+    def shift_batch_trajectory(self) -> None:
+        """``OptimalControlProblem::shiftBatchTrajectory``: receding-horizon shift of the stored batch iterates."""
+        _hcheck(host_lib().ocp_host_problem_shift_batch(self._h))
+
+
+class MpcLoop:
+    """Device-resident receding-horizon loop over B instances of one ``Problem`` (SURVEY.md 8f items
+    1 and 3): torch CUDA tensors in and out, no host copies between ticks.
+
+    The iterate ``x`` [B, N] lives on the device across ticks, which is what the reference's
+    persistent ``result_["x"]`` (SQPOptimizationSolver.cpp:215) amounts to for one instance; with
+    ``shift=True`` a tick first moves every stage one step towards the start of the horizon."""
+
+    def __init__(self, problem: "Problem", batch: int, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise NativeLibraryMissing("MpcLoop needs a CUDA device: there is no CPU path")
+        self.torch = torch
+        self.problem, self.B = problem, int(batch)
+        self.solver = problem.solver
+        self.device = torch.device(device if device is not None else "cuda:0")
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.x = torch.zeros((self.B, problem.N), **f64)
+        self.f = torch.zeros(self.B, **f64)
+        self.stats = torch.zeros((self.B, NSTATS), **f64)
+        self._bounds = [torch.from_numpy(np.ascontiguousarray(b)).to(self.device)
+                        for b in (problem.lbx, problem.ubx, problem.lbg, problem.ubg)]
+        self.ticks = 0
+
+    def _ptr(self, t, shape):
+        torch = self.torch
+        if t is None:
+            return None
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                and t.device == self.device and tuple(t.shape) == tuple(shape)):
+            raise ValueError(f"expected a contiguous float64 CUDA tensor of shape {tuple(shape)} on {self.device}")
+        return C.c_void_p(t.data_ptr())
+
+    def reset(self) -> None:
+        self.x.zero_()
+        self.ticks = 0
+
+    def tick(self, frames, references, shift: bool = False):
+        """One MPC tick: (optionally) shift the iterate, then ``step_num`` SQP steps from it with the
+        first frame of every instance pinned to ``frames`` [B, nf].  Asynchronous on torch's current
+        stream; returns (x [B, N], f [B], stats [B, NSTATS]) -- views of buffers the next tick overwrites."""
+        pr = self.problem
+        stream = C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        d_fr = self._ptr(frames, (self.B, pr.nf))
+        d_p = self._ptr(references, (self.B, pr.np_))
+        if shift and self.ticks > 0:
+            self.solver.shift_iterate_device(self.B, C.c_void_p(self.x.data_ptr()), stream)
+        lbx, ubx, lbg, ubg = (C.c_void_p(b.data_ptr()) for b in self._bounds)
+        self.solver.solve_batch_device(self.B, d_fr, d_p, lbx, ubx, lbg, ubg, C.c_void_p(self.x.data_ptr()),
+                                       C.c_void_p(self.f.data_ptr()), C.c_void_p(self.stats.data_ptr()), stream)
+        self.ticks += 1
+        return self.x, self.f, self.stats
+
+    def first_frame(self):
+        """Stage 0 of every trajectory [B, nf] (state and the control to apply): the reference's
+        ``getOptimalInputFirstFrame`` for the batch."""
+        return self.x[:, : self.problem.nf]
+
+    def frame(self, k: int):
+        nf = self.problem.nf
+        return self.x[:, k * nf:(k + 1) * nf]
 
 
 class KatProblem:

@@ -23,6 +23,16 @@
 
 namespace ocpb200 {
 // f -> stats column, after the objective kernel of the stage library has run
+// receding-horizon shift of the iterates: frame k <- frame k+1 (k < H-1), last frame repeated.
+// One CTA per instance; the row is staged in shared memory so the shift is in place.
+__global__ void shift_iterate_kernel(int nf, int N, double* __restrict__ x) {
+  extern __shared__ double row[];
+  double* xi = x + static_cast<size_t>(blockIdx.x) * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) row[j] = xi[j];
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += blockDim.x) xi[j] = row[j + nf < N ? j + nf : j];
+}
+
 __global__ void store_objective_kernel(int B, const double* __restrict__ f, double* __restrict__ stats) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) stats[size_t(b) * OCP_B200_NSTATS + OCP_B200_STAT_OBJECTIVE] = f[b];
@@ -695,6 +705,19 @@ int ocp_b200_solve_batch_device(ocp_b200_solver* s, int B, const double* d_frame
     CUDA_TRY(cudaGetLastError());
     s->launches++;
   }
+  return OCP_B200_OK;
+}
+
+int ocp_b200_shift_iterate_device(ocp_b200_solver* s, int B, double* d_x, void* stream) {
+  if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
+  if (B < 0 || (B > 0 && !d_x)) return fail(OCP_B200_ERR_INVALID, "bad arguments to shift_iterate");
+  if (B == 0 || s->N <= s->nf) return OCP_B200_OK;
+  const size_t smem = size_t(s->N) * sizeof(double);
+  if (smem > 48 * 1024) return fail(OCP_B200_ERR_UNSUPPORTED, "shift_iterate: trajectory longer than 6144 values");
+  CUDA_TRY(cudaSetDevice(s->device));
+  ocpb200::shift_iterate_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(s->nf, s->N, d_x);
+  CUDA_TRY(cudaGetLastError());
+  s->launches++;
   return OCP_B200_OK;
 }
 

@@ -80,6 +80,7 @@ class OptimalControlProblem {
   const std::vector<double>& getBatchObjectives() const { return batchObjective_; }
   const std::vector<double>& getBatchStats() const { return batchStats_; }
   void resetWarmStart();
+  void shiftBatchTrajectory();   // MPC tick: move every stored batch iterate one stage forward
 
   void setReference(const casadi::SX& reference);
   void setProblemName(const std::string& name) { problemName_ = name; }

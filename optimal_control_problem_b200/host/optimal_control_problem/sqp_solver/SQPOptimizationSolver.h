@@ -50,7 +50,7 @@ class SQPOptimizationSolver {
   int numParameters() const { return np_; }
   void resetIterate();
   // SQP schedule of the next solve: number of steps and step length (reference: fixed at construction)
-  void setSchedule(int stepNum, double alpha) { stepNum_ = stepNum; alpha_ = alpha; }
+  void setSchedule(int stepNum, double alpha);   // also pushed to the device handle when it exists
   double lastObjective() const { return densify(result_.at("f")).nonzeros().at(0); }
 
  private:

@@ -4,6 +4,7 @@
 // without the device library -- the CPU oracle uses only that half.
 #include "optimal_control_problem/OptimalControlProblem.h"
 
+#include <algorithm>
 #include <filesystem>
 
 using casadi::DM;
@@ -87,6 +88,19 @@ const std::vector<double>& OptimalControlProblem::computeOptimalTrajectoryBatch(
     throw std::runtime_error("Optimization failed: " + std::string(e.what()));
   }
   return batchTrajectory_;
+}
+
+// Receding-horizon shift of the stored batch iterates (MPC tick loop): frame k <- frame k+1 for
+// k < horizon-1, the last frame is repeated.  The reference keeps result_["x"] as the last solve
+// left it (SQPOptimizationSolver.cpp:215); this is the opt-in extension for a moving horizon.
+void OptimalControlProblem::shiftBatchTrajectory() {
+  const size_t nf = OCPConfigPtr_->getFrameSize();
+  const size_t N = nf * OCPConfigPtr_->getHorizon();
+  if (N <= nf) return;
+  for (int i = 0; i < batchSize_; ++i) {
+    double* xi = batchTrajectory_.data() + static_cast<size_t>(i) * N;
+    std::copy(xi + nf, xi + N, xi);
+  }
 }
 
 void OptimalControlProblem::resetWarmStart() {

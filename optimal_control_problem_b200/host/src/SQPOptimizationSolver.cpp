@@ -119,6 +119,14 @@ void SQPOptimizationSolver::applySettings() {
   check(ocp_b200_update_settings(handle_, &settings_), "ocp_b200_update_settings");
 }
 
+void SQPOptimizationSolver::setSchedule(int stepNum, double alpha) {
+  stepNum_ = stepNum;
+  alpha_ = alpha;
+  settings_.sqp_step_num = stepNum_;
+  settings_.sqp_alpha = alpha_;
+  if (handle_) check(ocp_b200_update_settings(handle_, &settings_), "ocp_b200_update_settings");
+}
+
 void SQPOptimizationSolver::resetIterate() { result_["x"] = DM::zeros(N_); result_["f"] = DM::zeros(1); }
 
 DMDict SQPOptimizationSolver::getOptimalSolution(const DMDict& arg) {

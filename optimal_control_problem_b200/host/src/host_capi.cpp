@@ -176,6 +176,12 @@ int ocp_host_problem_reset(void* h) {
   HOST_CATCH
 }
 
+int ocp_host_problem_shift_batch(void* h) {
+  HOST_TRY
+  static_cast<HostProblem*>(h)->ocp->shiftBatchTrajectory();
+  HOST_CATCH
+}
+
 int ocp_host_sample_inputs(const char* name, int B, unsigned long long seed, double* frames, double* refs) {
   HOST_TRY
   std::vector<double> f, r;
