@@ -40,6 +40,7 @@ struct PatternDev {
   // columns [0, tri_np) form the border (the reference parameters p), then tri_nb diagonal
   // blocks of tri_bs columns each; block rows are stored with an even pitch tri_ld >= tri_bs + 1
   int tri_ok, tri_np, tri_bs, tri_nb, tri_ld;
+  int stage_slots;         // block staging buffers per CTA when the factor is slab-resident (4, or 8 = a ring of 4 per chain)
   int kprog_entries;       // K-assembly program (null / 0: assemble by merging columns on the device)
   const KEntry* kprog;
   const KRun* kruns;

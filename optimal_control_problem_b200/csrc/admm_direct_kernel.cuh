@@ -58,6 +58,8 @@ enum ArrayId {
 __host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX || id == AR_PVAL || id == AR_D || id == AR_E; }
 __host__ __device__ constexpr bool big_in_smem(int id) { return id <= AR_IDX; }
 
+constexpr int kMaxRing = 8;   // ring slots per chain
+
 struct Work {
   double *x, *q, *b, *z, *y, *l, *u;
   signed char* ctype;
@@ -66,6 +68,11 @@ struct Work {
   double *Pval;
   double *stage;   // block staging buffers (null when the factor is in shared memory anyway)
   int stage_stride;
+  // asynchronous block ring of the sweeps (tri_twisted.cuh): the staging buffers split between the two
+  // chains, one mbarrier per slot, the phase parity of every slot kept across calls
+  unsigned long long* ring_bar;
+  unsigned* ring_phase;
+  int ring_slots;   // per chain; 0 = no ring
   double *Lp, *Dp, *Dp2, *S, *Sp, *xp, *piv;   // border: L_pk [np x N], D_p^-1 [np x (np+1)], scratch (two sets)
   int s_stride, sp_stride;
   long long* phase;   // cycle counters of CTA 0 (null unless profiling)
@@ -83,7 +90,7 @@ __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
     case AR_PVAL: return (size_t(P.nnz_p) + 1) & ~size_t(1);
     case AR_DINV: case AR_LSUB: return nb * bs * ld;
     case AR_IDX: return (size_t(P.idx_entries) * sizeof(idx_t) + 7) / 8;
-    case AR_STAGE: return 4 * ((bs * ld + 1) & ~size_t(1));
+    case AR_STAGE: return size_t(P.stage_slots > 0 ? P.stage_slots : 4) * ((bs * ld + 1) & ~size_t(1));
     case AR_LP: return (np * nb * bs + 1) & ~size_t(1);
     case AR_SCRATCH: return 3 * np * (np + 1) + 2 * ((bs * ld + 1) & ~size_t(1)) + 2 * ((np * bs + 1) & ~size_t(1)) +
                             ((np + 2) & ~size_t(1)) + 64;
@@ -482,6 +489,12 @@ __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work&
   if (P.tri_bs == 16 && P.tri_ld == 18) tri_factor_twisted<16>(P, W);
   else if (P.tri_bs == 20 && P.tri_ld == 22) tri_factor_twisted<20>(P, W);
   else tri_factor(P, W);
+  if (W.ring_slots > 0) {
+    // the sweeps read the new factor through the async proxy (bulk copies): order the generic-proxy
+    // stores of the factorisation before them
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncthreads();
+  }
 }
 __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
   if (P.tri_bs == 16 && P.tri_ld == 18) tri_solve_twisted<16>(P, W);
@@ -804,9 +817,19 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red_buf[2 * (kThreads / 32) * kRedWidth];
   __shared__ int s_inst;
+  __shared__ unsigned long long ring_bar[2 * kMaxRing];
+  __shared__ unsigned ring_phase[2];
   Work W;
   carve<kPlace>(W, P, smem_mask, reinterpret_cast<double*>(smem_raw),
                 kPlace == PLACE_SMEM ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles);
+  W.ring_bar = ring_bar; W.ring_phase = ring_phase;
+  W.ring_slots = (kPlace == PLACE_BIG && P.stage_slots >= 6) ? min(P.stage_slots / 2, kMaxRing) : 0;
+  if (kPlace == PLACE_BIG && threadIdx.x == 0) {
+    for (int i = 0; i < 2 * kMaxRing; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(ring_bar + i))));
+    ring_phase[0] = 0u; ring_phase[1] = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   PatternDev PL = P;
   if (kPlace != PLACE_MIXED || (smem_mask >> AR_IDX & 1u)) {
     // index structures move into shared memory once per CTA (same offsets as the global arena)

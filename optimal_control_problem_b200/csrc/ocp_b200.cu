@@ -349,12 +349,17 @@ int plan_launch(ocp_b200_solver* s) {
     const char* env = std::getenv("OCP_B200_PLAN");
     size_t multi_smem = 0, multi_slab = 0, big_smem = 0, big_slab = 0, all = 0;
     const int stage_id = D::plan_stage_array();   // not allocated by the all-shared-memory plan
-    for (int id = 0; id < count; ++id) {
-      const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
-      if (id != stage_id) all += sz;
-      (D::plan_multi_in_smem(id) ? multi_smem : multi_slab) += sz;
-      (D::plan_big_in_smem(id) ? big_smem : big_slab) += sz;
-    }
+    auto measure = [&]() {
+      multi_smem = multi_slab = big_smem = big_slab = all = 0;
+      for (int id = 0; id < count; ++id) {
+        const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
+        if (id != stage_id) all += sz;
+        (D::plan_multi_in_smem(id) ? multi_smem : multi_slab) += sz;
+        (D::plan_big_in_smem(id) ? big_smem : big_slab) += sz;
+      }
+    };
+    s->pat.stage_slots = 4;
+    measure();
     auto make_plan = [&](int place, LaunchPlan& L) -> int {
       D::KernelInfo kx{};
       CUDA_TRY(D::kernel_info(place, &kx));
@@ -393,7 +398,16 @@ int plan_launch(ocp_b200_solver* s) {
     const bool fits_multi = (multi_smem * sizeof(double) + km.static_smem + 1024) * 2 <= size_t(228) * 1024;
     D::KernelInfo kb{};
     CUDA_TRY(D::kernel_info(3, &kb));
-    const bool fits_big = big_smem * sizeof(double) + kb.static_smem <= size_t(max_optin);
+    bool fits_big = big_smem * sizeof(double) + kb.static_smem <= size_t(max_optin);
+    if (!fits_all && !fits_multi && fits_big) {
+      // the 1-CTA/SM slab plan is the only one: widen the staging area to a ring of 4 blocks per
+      // sweep chain (asynchronous bulk copies, tri_twisted.cuh) when shared memory allows
+      int want = 8;
+      if (const char* e = std::getenv("OCP_B200_STAGE_SLOTS")) want = std::max(4, std::min(16, std::atoi(e)));
+      s->pat.stage_slots = want;
+      measure();
+      if (big_smem * sizeof(double) + kb.static_smem > size_t(max_optin)) { s->pat.stage_slots = 4; measure(); }
+    }
     int deep = fits_all ? 1 : (fits_big ? 3 : 0), wide = fits_multi ? 2 : deep;
     if (env && !std::strcmp(env, "multi") && fits_multi) deep = wide = 2;
     else if (env && !std::strcmp(env, "mixed")) deep = wide = 0;

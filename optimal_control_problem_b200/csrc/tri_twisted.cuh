@@ -147,13 +147,70 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   }
 }
 
+// ---- asynchronous block ring -------------------------------------------------------------
+// When the factor lives in the global slab and a block row no longer fits a three-deep register
+// prefetch, each chain warp streams its blocks through a ring of shared-memory slots with 1-D
+// bulk copies (cp.async.bulk, completion counted on one mbarrier per slot): lane 0 keeps
+// ring_slots copies in flight, every lane waits on the slot's barrier before reading it.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ring_issue(double* dst, const double* src, uint32_t bytes, unsigned long long* bar) {
+  const uint32_t b = smem_addr(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void ring_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t b = smem_addr(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// one sweep stage out of a ring slot, one lane per block row (CPL == BS): every shared-memory load is
+// issued before the first FMA -- the stream of a single warp is in-order, a load placed behind an
+// FMA that waits for its operands costs a full shared-memory latency
+template <int BS, bool kColumn>
+__device__ __forceinline__ void ring_stage(const double* __restrict__ blk, const double* __restrict__ src,
+                                           double* __restrict__ dst, bool writer, bool src_vec) {
+  constexpr int ld = BS + 2;
+  static_assert(TriCfg<BS>::LPR == 1 && BS % 4 == 0, "one lane per row");
+  double lv[BS], sv[BS];
+  if (!kColumn) {
+    const double2* p2 = reinterpret_cast<const double2*>(blk);
+#pragma unroll
+    for (int i = 0; i < BS / 2; ++i) { const double2 v = p2[i]; lv[2 * i] = v.x; lv[2 * i + 1] = v.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) lv[i] = blk[i * ld];
+  }
+  if (src_vec) {
+    const double2* q2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+    for (int i = 0; i < BS / 2; ++i) { const double2 v = q2[i]; sv[2 * i] = v.x; sv[2 * i + 1] = v.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) sv[i] = src[i];
+  }
+  const double old = writer ? *dst : 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int c = 0; c < BS; c += 4) {
+    s0 = fma(lv[c], sv[c], s0); s1 = fma(lv[c + 1], sv[c + 1], s1);
+    s2 = fma(lv[c + 2], sv[c + 2], s2); s3 = fma(lv[c + 3], sv[c + 3], s3);
+  }
+  if (writer) *dst = old - ((s0 + s1) + (s2 + s3));
+  __syncwarp();
+}
+
 // `count` consecutive sweep stages by one warp: stage i multiplies slot (slot0 + i*dslot) with
 // source block (src0 + i*dblk) and subtracts from destination block (dst0 + i*dblk).
 // kColumn = false: dst[r] -= sum_c M[r][c] src[c]   (forward sweeps)
 // kColumn = true : dst[r] -= sum_c M[c][r] src[c]   (backward sweeps)
 template <int BS, bool kColumn>
 __device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/, int slot0, int dslot, int dst0, int src0,
-                                          int dblk, int count, int lane) {
+                                          int dblk, int count, int lane, int chain) {
   constexpr int CPL = TriCfg<BS>::CPL, LPR = TriCfg<BS>::LPR, ld = BS + 2;
   const int row = lane / LPR, half = lane % LPR;
   const bool act = row < BS;
@@ -175,6 +232,31 @@ __device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/,
       for (int i = 0; i < CPL; ++i) dst[i] = p[i * ld];
     }
   };
+  if constexpr (CPL > 8) if (W.ring_slots >= 2) {
+    // slab-resident factor, wide block rows: blocks arrive through the shared-memory ring
+    const int R = W.ring_slots, stride = W.stage_stride;
+    double* ring = W.stage + chain * R * stride;
+    unsigned long long* bars = W.ring_bar + chain * kMaxRing;
+    constexpr uint32_t bytes = BS * ld * sizeof(double);
+    const double* gp = W.Lsub + size_t(slot0) * BS * ld;
+    uint32_t ph = W.ring_phase[chain];
+    if (lane == 0)
+      for (int i = 0; i < R && i < count; ++i) ring_issue(ring + i * stride, gp + i * dl, bytes, bars + i);
+    const int off = kColumn ? (half * CPL) * ld + rr : rr * ld + half * CPL;
+    const bool src_vec = (reinterpret_cast<unsigned long long>(srcp) & 15ULL) == 0ULL;   // uniform: np even
+    int s = 0;
+    for (int i = 0; i < count; ++i) {
+      ring_wait(bars + s, (ph >> s) & 1u);
+      ph ^= 1u << s;
+      ring_stage<BS, kColumn>(ring + s * stride + off, srcp, dstp, writer, src_vec);   // ends with __syncwarp
+      if (lane == 0 && i + R < count) ring_issue(ring + s * stride, gp + (i + R) * dl, bytes, bars + s);
+      srcp += db; dstp += db;
+      s = s + 1 == R ? 0 : s + 1;
+    }
+    if (lane == 0) W.ring_phase[chain] = ph;
+    __syncwarp();
+    return;
+  }
   if (W.stage != nullptr && CPL <= 8) {
     // slab-resident factor: three register buffers, block rows requested two stages ahead (an L2
     // round trip under load is longer than one stage)
@@ -231,12 +313,12 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   }
   // forward: top chain y_k = b_k - L_k y_{k-1} (k = 1..mid-1) and bottom chain
   // y_k = b_k - U_k y_{k+1} (k = nb-2..mid+1) on two warps, then both contributions to block mid
-  if (warp == 0) run_chain<BS, false>(W, bx, ld, 1, 1, 1, 0, 1, mid - 1, lane);
-  else if (warp == 1) run_chain<BS, false>(W, bx, ld, nb - 1, -1, nb - 2, nb - 1, -1, nb - 2 - mid, lane);
+  if (warp == 0) run_chain<BS, false>(W, bx, ld, 1, 1, 1, 0, 1, mid - 1, lane, 0);
+  else if (warp == 1) run_chain<BS, false>(W, bx, ld, nb - 1, -1, nb - 2, nb - 1, -1, nb - 2 - mid, lane, 1);
   __syncthreads();
   if (warp == 0) {
-    if (mid >= 1) run_chain<BS, false>(W, bx, ld, mid, 1, mid, mid - 1, 1, 1, lane);
-    if (mid + 1 < nb) run_chain<BS, false>(W, bx, ld, mid + 1, 1, mid, mid + 1, 1, 1, lane);
+    if (mid >= 1) run_chain<BS, false>(W, bx, ld, mid, 1, mid, mid - 1, 1, 1, lane, 0);
+    if (mid + 1 < nb) run_chain<BS, false>(W, bx, ld, mid + 1, 1, mid, mid + 1, 1, 1, lane, 0);
   }
   __syncthreads();
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
@@ -325,8 +407,8 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
   // backward, from block mid outwards: x_k = c_k - L_{k+1}' x_{k+1} (k = mid-1..0) and
   // x_k = c_k - U_{k-1}' x_{k-1} (k = mid+1..nb-1)
-  if (warp == 0) run_chain<BS, true>(W, bx, ld, mid, -1, mid - 1, mid, -1, mid, lane);
-  else if (warp == 1) run_chain<BS, true>(W, bx, ld, mid + 1, 1, mid + 1, mid, 1, nb - 1 - mid, lane);
+  if (warp == 0) run_chain<BS, true>(W, bx, ld, mid, -1, mid - 1, mid, -1, mid, lane, 0);
+  else if (warp == 1) run_chain<BS, true>(W, bx, ld, mid + 1, 1, mid + 1, mid, 1, nb - 1 - mid, lane, 1);
   __syncthreads();
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
 }
