@@ -31,6 +31,7 @@
 #pragma once
 
 #include "admm_common.cuh"
+#include "block_ring.cuh"
 
 namespace ocpb200 {
 namespace direct {
@@ -476,12 +477,215 @@ __device__ inline void tri_solve(const PatternDev& P, const Work& W) {
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
 }
 
+// K x = b in place with the factor STREAMED from the global slab (the problem is too large for the
+// factor to stay on chip).  Every block of the factor is used exactly once per phase, so the three
+// block phases -- forward sweep over L_1..L_{nb-1}, diagonal phase over D_0^-1..D_{nb-1}^-1, backward
+// sweep over L_{nb-1}..L_1 -- pull their blocks through the shared-memory ring (block_ring.cuh: bulk
+// copies, ring_slots blocks in flight) and read them from shared memory, which also makes the
+// transposed access of the backward sweep conflict-free instead of uncoalesced.  Four lanes per block
+// row as in coop_sweep; one named barrier per stage.  kBS > 0: compile-time block size (pitch kBS + 2),
+// every loop unrolled and all shared-memory loads of a stage issued before its first FMA; kBS == 0:
+// any block size.
+template <int kBS>
+__device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int np = P.tri_np, nb = P.tri_nb;
+  const int bs = kBS > 0 ? kBS : P.tri_bs, ld = kBS > 0 ? kBS + 2 : P.tri_ld, N = nb * bs;
+  double* bx = W.b + np;
+  const int R = W.ring_slots, stride = W.stage_stride;
+  const uint32_t bytes = static_cast<uint32_t>(bs * ld * sizeof(double));
+  const int nthr = ((4 * bs + 31) / 32) * 32;   // participating threads (whole warps)
+  const int row = tid >> 2, sub = tid & 3;
+  const bool part = tid < nthr, act = part && row < bs;
+  const int rr = act ? row : 0;
+  constexpr int kPer = kBS > 0 ? (kBS + 3) / 4 : 16;   // columns per lane (bs <= 64)
+  uint32_t ph = W.ring_phase[0];   // identical in every participating thread
+  OCP_B200_FINE_CLOCK(clk, W.phase);
+
+  // one block phase: stage t uses block g0 + t * gstep of `base`
+  auto prologue = [&](const double* base, int g0, int gstep, int count) {
+    if (tid == 0)
+      for (int i = 0; i < R && i < count; ++i)
+        ring_issue(W.stage + i * stride, base + size_t(g0 + i * gstep) * bs * ld, bytes, W.ring_bar + i);
+  };
+  auto refill = [&](const double* base, int g0, int gstep, int count, int t, int s) {
+    if (tid == 0 && t + R < count)
+      ring_issue(W.stage + s * stride, base + size_t(g0 + (t + R) * gstep) * bs * ld, bytes, W.ring_bar + s);
+  };
+  // sum over this lane's columns c = sub, sub + 4, ... of M[rr][c] src[c] (or M[c][rr] src[c]),
+  // combined over the four lanes of the row
+  auto block_dot = [&](const double* blk, const double* src, bool column) {
+    double mv[kPer], sv[kPer];
+    const double* mp = column ? blk + rr : blk + rr * ld;
+    const int ms = column ? ld : 1;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int c = sub + 4 * i;
+      const bool ok = c < bs;
+      mv[i] = ok ? mp[c * ms] : 0.0;
+      sv[i] = ok ? src[c] : 0.0;
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPer; i += 3) {
+      s0 = fma(mv[i], sv[i], s0);
+      if (i + 1 < kPer) s1 = fma(mv[i + 1], sv[i + 1], s1);
+      if (i + 2 < kPer) s2 = fma(mv[i + 2], sv[i + 2], s2);
+    }
+    double sum = (s0 + s1) + s2;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    return sum;
+  };
+
+  // forward sweep: y_k = b_k - L_k y_{k-1}, k = 1..nb-1
+  if (part && nb >= 2) {
+    const int count = nb - 1;
+    prologue(W.Lsub, 1, 1, count);
+    int s = 0;
+    for (int t = 0; t < count; ++t) {
+      ring_wait(W.ring_bar + s, (ph >> s) & 1u);
+      ph ^= 1u << s;
+      const double old = (act && sub == 0) ? bx[(t + 1) * bs + row] : 0.0;
+      const double sum = block_dot(W.stage + s * stride, bx + t * bs, false);
+      if (act && sub == 0) bx[(t + 1) * bs + row] = old - sum;
+      asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
+      refill(W.Lsub, 1, 1, count, t, s);
+      s = s + 1 == R ? 0 : s + 1;
+    }
+  }
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
+
+  // border: y_p = b_p - sum_k L_pk y_k.  L_p [np x N] is streamed once: every thread owns a strided set
+  // of column pairs and keeps eight border rows' partial sums, all eight 16-byte loads of a column pair
+  // issued together; the warps' sums meet in shared memory in a fixed order.  Then x_p = D_p^-1 y_p.
+  if (np > 0) {
+    const bool vec = (N & 1) == 0 && (reinterpret_cast<unsigned long long>(bx) & 15ULL) == 0ULL &&
+                     (reinterpret_cast<unsigned long long>(W.Lp) & 15ULL) == 0ULL;
+    double* part_sums = W.S;   // factor scratch, free during a solve: [warp][8]
+    for (int r0 = 0; r0 < np; r0 += 8) {
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (vec) {
+        const double2* y2 = reinterpret_cast<const double2*>(bx);
+#pragma unroll 2
+        for (int j = tid; j < N / 2; j += T) {
+          double2 v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            v[q] = r0 + q < np ? reinterpret_cast<const double2*>(W.Lp + size_t(r0 + q) * N)[j] : make_double2(0.0, 0.0);
+          const double2 y = y2[j];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = fma(v[q].x, y.x, fma(v[q].y, y.y, acc[q]));
+        }
+      } else {
+        for (int j = tid; j < N; j += T) {
+          const double y = bx[j];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (r0 + q < np) acc[q] = fma(W.Lp[size_t(r0 + q) * N + j], y, acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) part_sums[warp * 8 + q] = acc[q];
+      }
+      __syncthreads();
+      if (tid < 8 && r0 + tid < np) {
+        double sacc = 0.0;
+        for (int w = 0; w < nw; ++w) sacc += part_sums[w * 8 + tid];
+        W.xp[r0 + tid] = W.b[r0 + tid] - sacc;
+      }
+      __syncthreads();
+    }
+    if (tid < np) {
+      double sacc = 0.0;
+      for (int c = 0; c < np; ++c) sacc += W.Dp[tid * (np + 1) + c] * W.xp[c];
+      W.b[tid] = sacc;
+    }
+    __syncthreads();
+  }
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
+
+  // diagonal phase: c_k = D_k^-1 y_k - L_pk' x_p, block by block through the ring; the L_p values of
+  // the next block are requested before the current block is multiplied
+  if (part) {
+    const int count = nb;
+    prologue(W.Dinv, 0, 1, count);
+    constexpr int kMaxLp = 8;   // border rows per lane: np <= 32
+    const bool lp_regs = np <= 4 * kMaxLp;
+    double lpn[kMaxLp] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    auto fetch_lp = [&](int k) {
+#pragma unroll
+      for (int i = 0; i < kMaxLp; ++i) {
+        const int p = sub + 4 * i;
+        lpn[i] = (act && p < np) ? W.Lp[size_t(p) * N + k * bs + row] : 0.0;
+      }
+    };
+    if (lp_regs) fetch_lp(0);
+    double xpv[kMaxLp];
+#pragma unroll
+    for (int i = 0; i < kMaxLp; ++i) xpv[i] = (lp_regs && sub + 4 * i < np) ? W.b[sub + 4 * i] : 0.0;
+    int s = 0;
+    for (int k = 0; k < count; ++k) {
+      double corr = 0.0, corr1 = 0.0;
+      if (lp_regs) {
+#pragma unroll
+        for (int i = 0; i < kMaxLp; i += 2) { corr = fma(lpn[i], xpv[i], corr); corr1 = fma(lpn[i + 1], xpv[i + 1], corr1); }
+        corr += corr1;
+        if (k + 1 < count) fetch_lp(k + 1);
+      } else if (act) {
+        for (int p = sub; p < np; p += 4) corr = fma(W.Lp[size_t(p) * N + k * bs + row], W.b[p], corr);
+      }
+      ring_wait(W.ring_bar + s, (ph >> s) & 1u);
+      ph ^= 1u << s;
+      double v = block_dot(W.stage + s * stride, bx + k * bs, false);
+      corr += __shfl_xor_sync(0xffffffffu, corr, 1);
+      corr += __shfl_xor_sync(0xffffffffu, corr, 2);
+      asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");   // every row has read y_k
+      if (act && sub == 0) bx[k * bs + row] = v - corr;
+      refill(W.Dinv, 0, 1, count, k, s);
+      s = s + 1 == R ? 0 : s + 1;
+    }
+  }
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
+
+  // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}, k = nb-2..0
+  if (part && nb >= 2) {
+    const int count = nb - 1;
+    prologue(W.Lsub, nb - 1, -1, count);
+    int s = 0;
+    for (int t = 0; t < count; ++t) {
+      const int blkid = nb - 1 - t;
+      ring_wait(W.ring_bar + s, (ph >> s) & 1u);
+      ph ^= 1u << s;
+      const double old = (act && sub == 0) ? bx[(blkid - 1) * bs + row] : 0.0;
+      const double sum = block_dot(W.stage + s * stride, bx + blkid * bs, true);
+      if (act && sub == 0) bx[(blkid - 1) * bs + row] = old - sum;
+      asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
+      refill(W.Lsub, nb - 1, -1, count, t, s);
+      s = s + 1 == R ? 0 : s + 1;
+    }
+  }
+  if (tid == 0) W.ring_phase[0] = ph;
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
+}
+
 }  // namespace direct
 }  // namespace ocpb200
 #include "tri_fast.cuh"
 #include "tri_twisted.cuh"
 namespace ocpb200 {
 namespace direct {
+
+// block sizes with exact-size (compile-time) factorisation and sweeps: tri_fast.cuh / tri_twisted.cuh
+__device__ __forceinline__ bool exact_block_code(const PatternDev& P) {
+  return (P.tri_bs == 16 && P.tri_ld == 18) || (P.tri_bs == 20 && P.tri_ld == 22);
+}
 
 // block-size dispatch (uniform across the CTA)
 __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work& W) {
@@ -499,6 +703,11 @@ __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work&
 __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
   if (P.tri_bs == 16 && P.tri_ld == 18) tri_solve_twisted<16>(P, W);
   else if (P.tri_bs == 20 && P.tri_ld == 22) tri_solve_twisted<20>(P, W);
+  else if (W.ring_slots > 0) {
+    if (P.tri_bs == 36 && P.tri_ld == 38) tri_solve_stream<36>(P, W);
+    else if (P.tri_bs == 24 && P.tri_ld == 26) tri_solve_stream<24>(P, W);
+    else tri_solve_stream<0>(P, W);
+  }
   else tri_solve(P, W);
 }
 
@@ -823,8 +1032,14 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
   carve<kPlace>(W, P, smem_mask, reinterpret_cast<double*>(smem_raw),
                 kPlace == PLACE_SMEM ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles);
   W.ring_bar = ring_bar; W.ring_phase = ring_phase;
+  // PLACE_BIG: the staging area is split between the two chains of the twisted sweeps; PLACE_MIXED
+  // (generic block code, one chain): the whole area is one ring, provided it is in shared memory and
+  // the factor is not
   W.ring_slots = (kPlace == PLACE_BIG && P.stage_slots >= 6) ? min(P.stage_slots / 2, kMaxRing) : 0;
-  if (kPlace == PLACE_BIG && threadIdx.x == 0) {
+  if (kPlace == PLACE_MIXED && !exact_block_code(P) && (smem_mask >> AR_STAGE & 1u) && !(smem_mask >> AR_LSUB & 1u) &&
+      !(smem_mask >> AR_DINV & 1u))
+    W.ring_slots = min(P.stage_slots > 0 ? P.stage_slots : 4, kMaxRing);
+  if ((kPlace == PLACE_BIG || kPlace == PLACE_MIXED) && threadIdx.x == 0) {
     for (int i = 0; i < 2 * kMaxRing; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(ring_bar + i))));
     ring_phase[0] = 0u; ring_phase[1] = 0u;

@@ -1,6 +1,7 @@
 // direct_launch.h -- host-side entry points of the instantiations of admm_direct_kernel, each
 // compiled in its own translation unit (they are large; nvcc builds them in parallel).
 #pragma once
+#include <vector>
 
 #include "admm_common.cuh"
 
@@ -22,6 +23,7 @@ int plan_array_count();
 bool plan_multi_in_smem(int id);
 bool plan_big_in_smem(int id);
 int plan_stage_array();
+void plan_mixed_priority(std::vector<int>& order);   // array ids, most deserving of shared memory first
 
 }  // namespace direct
 }  // namespace ocpb200

@@ -377,7 +377,16 @@ int plan_launch(ocp_b200_solver* s) {
       } else {
         size_t avail = (size_t(max_optin) - kx.static_smem) / sizeof(double), used = 0, slab = 0;
         uint32_t mask = 0;
-        for (int id = 0; id < count; ++id) {
+        // mixed placement: shared memory goes first to what is accessed at random or sits on the
+        // sequential path (solve vector, x, w, the block ring, the border scratch); vectors that are
+        // only streamed row by row (z, y, l, u) and the matrices follow while space lasts
+        std::vector<int> order;
+        if (place == 1) {
+          for (int id = 0; id < count; ++id) order.push_back(id);
+        } else {
+          D::plan_mixed_priority(order);
+        }
+        for (int id : order) {
           const size_t sz = (place == 1 && id == stage_id) ? 0 : ((D::plan_array_doubles(P, id) + 1) & ~size_t(1));
           if (place == 1 || used + sz <= avail) { mask |= 1u << id; used += sz; }
           else slab += sz;
