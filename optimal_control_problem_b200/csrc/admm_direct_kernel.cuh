@@ -502,15 +502,28 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   uint32_t ph = W.ring_phase[0];   // identical in every participating thread
   OCP_B200_FINE_CLOCK(clk, W.phase);
 
-  // one block phase: stage t uses block g0 + t * gstep of `base`
-  auto prologue = [&](const double* base, int g0, int gstep, int count) {
-    if (tid == 0)
-      for (int i = 0; i < R && i < count; ++i)
-        ring_issue(W.stage + i * stride, base + size_t(g0 + i * gstep) * bs * ld, bytes, W.ring_bar + i);
+  // The three block phases form ONE stream of G = 2 (nb - 1) + nb blocks, so the ring never drains
+  // between them (and keeps filling during the border phase): stream position g -> block address.
+  // Ring slots: the staging area, then the two block-sized scratch buffers of the factorisation.
+  const int G = 2 * (nb - 1) + nb;
+  const size_t blk_doubles = size_t(bs) * ld;
+  auto gaddr = [&](int g) -> const double* {
+    if (g < nb - 1) return W.Lsub + size_t(1 + g) * blk_doubles;
+    g -= nb - 1;
+    if (g < nb) return W.Dinv + size_t(g) * blk_doubles;
+    g -= nb;
+    return W.Lsub + size_t(nb - 1 - g) * blk_doubles;
   };
-  auto refill = [&](const double* base, int g0, int gstep, int count, int t, int s) {
-    if (tid == 0 && t + R < count)
-      ring_issue(W.stage + s * stride, base + size_t(g0 + (t + R) * gstep) * bs * ld, bytes, W.ring_bar + s);
+  auto slot_ptr = [&](int sl) -> double* {
+    return sl < P.stage_slots ? W.stage + sl * stride : W.S + (sl - P.stage_slots) * W.s_stride;
+  };
+  if (tid == 0)
+    for (int i = 0; i < R && i < G; ++i) ring_issue(slot_ptr(i), gaddr(i), bytes, W.ring_bar + i);
+  int g = 0, s = 0;   // stream position, ring slot
+  auto advance = [&]() {   // after the stage's barrier: the slot is free, request the block R positions ahead
+    if (tid == 0 && g + R < G) ring_issue(slot_ptr(s), gaddr(g + R), bytes, W.ring_bar + s);
+    ++g;
+    s = s + 1 == R ? 0 : s + 1;
   };
   // sum over this lane's columns c = sub, sub + 4, ... of M[rr][c] src[c] (or M[c][rr] src[c]),
   // combined over the four lanes of the row
@@ -539,19 +552,15 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   };
 
   // forward sweep: y_k = b_k - L_k y_{k-1}, k = 1..nb-1
-  if (part && nb >= 2) {
-    const int count = nb - 1;
-    prologue(W.Lsub, 1, 1, count);
-    int s = 0;
-    for (int t = 0; t < count; ++t) {
+  if (part) {
+    for (int t = 0; t < nb - 1; ++t) {
       ring_wait(W.ring_bar + s, (ph >> s) & 1u);
       ph ^= 1u << s;
       const double old = (act && sub == 0) ? bx[(t + 1) * bs + row] : 0.0;
-      const double sum = block_dot(W.stage + s * stride, bx + t * bs, false);
+      const double sum = block_dot(slot_ptr(s), bx + t * bs, false);
       if (act && sub == 0) bx[(t + 1) * bs + row] = old - sum;
       asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
-      refill(W.Lsub, 1, 1, count, t, s);
-      s = s + 1 == R ? 0 : s + 1;
+      advance();
     }
   }
   __syncthreads();
@@ -563,8 +572,21 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   if (np > 0) {
     const bool vec = (N & 1) == 0 && (reinterpret_cast<unsigned long long>(bx) & 15ULL) == 0ULL &&
                      (reinterpret_cast<unsigned long long>(W.Lp) & 15ULL) == 0ULL;
-    double* part_sums = W.S;   // factor scratch, free during a solve: [warp][8]
-    for (int r0 = 0; r0 < np; r0 += 8) {
+    double* part_sums = W.Dp2;   // factor scratch, free during a solve: [warp][8]
+    const bool wide_border = 2 * np * (np + 1) >= nw * 8;
+    if (!wide_border) {   // small border: a warp per row
+      for (int r = warp; r < np; r += nw) {
+        double sacc = 0.0;
+        const double* rowp = W.Lp + size_t(r) * N;
+#pragma unroll 8
+        for (int j = lane; j < N; j += 32) sacc += rowp[j] * bx[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) W.xp[r] = W.b[r] - sacc;
+      }
+      __syncthreads();
+    }
+    for (int r0 = 0; wide_border && r0 < np; r0 += 8) {
       double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (vec) {
         const double2* y2 = reinterpret_cast<const double2*>(bx);
@@ -613,7 +635,6 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   // the next block are requested before the current block is multiplied
   if (part) {
     const int count = nb;
-    prologue(W.Dinv, 0, 1, count);
     constexpr int kMaxLp = 8;   // border rows per lane: np <= 32
     const bool lp_regs = np <= 4 * kMaxLp;
     double lpn[kMaxLp] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -628,7 +649,6 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
     double xpv[kMaxLp];
 #pragma unroll
     for (int i = 0; i < kMaxLp; ++i) xpv[i] = (lp_regs && sub + 4 * i < np) ? W.b[sub + 4 * i] : 0.0;
-    int s = 0;
     for (int k = 0; k < count; ++k) {
       double corr = 0.0, corr1 = 0.0;
       if (lp_regs) {
@@ -641,33 +661,28 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
       }
       ring_wait(W.ring_bar + s, (ph >> s) & 1u);
       ph ^= 1u << s;
-      double v = block_dot(W.stage + s * stride, bx + k * bs, false);
+      double v = block_dot(slot_ptr(s), bx + k * bs, false);
       corr += __shfl_xor_sync(0xffffffffu, corr, 1);
       corr += __shfl_xor_sync(0xffffffffu, corr, 2);
       asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");   // every row has read y_k
       if (act && sub == 0) bx[k * bs + row] = v - corr;
-      refill(W.Dinv, 0, 1, count, k, s);
-      s = s + 1 == R ? 0 : s + 1;
+      advance();
     }
   }
   __syncthreads();
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
 
   // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}, k = nb-2..0
-  if (part && nb >= 2) {
-    const int count = nb - 1;
-    prologue(W.Lsub, nb - 1, -1, count);
-    int s = 0;
-    for (int t = 0; t < count; ++t) {
+  if (part) {
+    for (int t = 0; t < nb - 1; ++t) {
       const int blkid = nb - 1 - t;
       ring_wait(W.ring_bar + s, (ph >> s) & 1u);
       ph ^= 1u << s;
       const double old = (act && sub == 0) ? bx[(blkid - 1) * bs + row] : 0.0;
-      const double sum = block_dot(W.stage + s * stride, bx + blkid * bs, true);
+      const double sum = block_dot(slot_ptr(s), bx + blkid * bs, true);
       if (act && sub == 0) bx[(blkid - 1) * bs + row] = old - sum;
       asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
-      refill(W.Lsub, nb - 1, -1, count, t, s);
-      s = s + 1 == R ? 0 : s + 1;
+      advance();
     }
   }
   if (tid == 0) W.ring_phase[0] = ph;
@@ -1038,7 +1053,7 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
   W.ring_slots = (kPlace == PLACE_BIG && P.stage_slots >= 6) ? min(P.stage_slots / 2, kMaxRing) : 0;
   if (kPlace == PLACE_MIXED && !exact_block_code(P) && (smem_mask >> AR_STAGE & 1u) && !(smem_mask >> AR_LSUB & 1u) &&
       !(smem_mask >> AR_DINV & 1u))
-    W.ring_slots = min(P.stage_slots > 0 ? P.stage_slots : 4, kMaxRing);
+    W.ring_slots = min((P.stage_slots > 0 ? P.stage_slots : 4) + ((smem_mask >> AR_SCRATCH & 1u) ? 2 : 0), kMaxRing);
   if ((kPlace == PLACE_BIG || kPlace == PLACE_MIXED) && threadIdx.x == 0) {
     for (int i = 0; i < 2 * kMaxRing; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(ring_bar + i))));
