@@ -23,7 +23,8 @@ int plan_array_count();
 bool plan_multi_in_smem(int id);
 bool plan_big_in_smem(int id);
 int plan_stage_array();
-void plan_mixed_priority(std::vector<int>& order);   // array ids, most deserving of shared memory first
+void plan_mixed_priority(std::vector<int>& order);
+bool plan_is_factor_array(int id);   // D^-1, L, L_p blocks   // array ids, most deserving of shared memory first
 
 }  // namespace direct
 }  // namespace ocpb200

@@ -41,6 +41,7 @@ int plan_array_count() { return AR_COUNT; }
 bool plan_multi_in_smem(int id) { return multi_in_smem(id); }
 bool plan_big_in_smem(int id) { return big_in_smem(id); }
 int plan_stage_array() { return AR_STAGE; }
+bool plan_is_factor_array(int id) { return id == AR_DINV || id == AR_LSUB || id == AR_LP; }
 void plan_mixed_priority(std::vector<int>& order) {
   order = {AR_B, AR_X, AR_W, AR_CTYPE, AR_Q, AR_STAGE, AR_SCRATCH, AR_Z, AR_Y, AR_L, AR_U, AR_D, AR_E,
            AR_AVAL, AR_IDX, AR_PVAL, AR_LP, AR_DINV, AR_LSUB, AR_DX, AR_DY};

@@ -386,9 +386,13 @@ int plan_launch(ocp_b200_solver* s) {
         } else {
           D::plan_mixed_priority(order);
         }
+        // OCP_B200_FORCE_STREAM keeps the factor in the global slab even when it would fit (tests of the
+        // streamed solve on small problems)
+        const bool force_stream = place == 0 && std::getenv("OCP_B200_FORCE_STREAM") != nullptr;
         for (int id : order) {
           const size_t sz = (place == 1 && id == stage_id) ? 0 : ((D::plan_array_doubles(P, id) + 1) & ~size_t(1));
-          if (place == 1 || used + sz <= avail) { mask |= 1u << id; used += sz; }
+          const bool keep_out = force_stream && D::plan_is_factor_array(id);
+          if (!keep_out && (place == 1 || used + sz <= avail)) { mask |= 1u << id; used += sz; }
           else slab += sz;
         }
         L.smem_mask = mask;
@@ -408,7 +412,8 @@ int plan_launch(ocp_b200_solver* s) {
     D::KernelInfo kb{};
     CUDA_TRY(D::kernel_info(3, &kb));
     bool fits_big = big_smem * sizeof(double) + kb.static_smem <= size_t(max_optin);
-    if (!fits_all && !fits_multi && fits_big) {
+    const bool forced_big = env && !std::strcmp(env, "big");
+    if (fits_big && ((!fits_all && !fits_multi) || forced_big)) {
       // the 1-CTA/SM slab plan is the only one: widen the staging area to a ring of 4 blocks per
       // sweep chain (asynchronous bulk copies, tri_twisted.cuh) when shared memory allows
       int want = 8;

@@ -443,3 +443,36 @@ def test_iteration_limit_statuses(problems, native, max_iter, eps):
         assert oinfo[0] in (native.QP_MAX_ITER, native.QP_SOLVED_INACCURATE, native.QP_SOLVED)
         assert info[b, native.INFO["iters"]] == oinfo[1] <= max_iter
         assert rel_err(x[b], ox) < REL_SOLUTION
+
+
+@pytest.mark.parametrize("name,horizon,plan", [
+    ("cartpole", 9, "mixed"),      # blocks of 15 columns (odd size, generic code), border of 4: narrow-border path
+    ("cartpole", 27, "mixed"),
+    ("centroidal", 6, "mixed"),    # blocks of 36 (compile-time streamed code), border of 24: wide-border path
+    ("cartpole", 40, "big"),       # blocks of 20, twisted sweeps through the two-chain ring
+])
+def test_streamed_factor_paths_match_oracle(native, monkeypatch, name, horizon, plan):
+    """The slab-resident (streamed) factor code on problems small enough to compare quickly: the launch
+    plan is forced and the factor kept out of shared memory (OCP_B200_PLAN / OCP_B200_FORCE_STREAM are
+    read when the handle is created)."""
+    monkeypatch.setenv("OCP_B200_PLAN", plan)
+    monkeypatch.setenv("OCP_B200_FORCE_STREAM", "1")
+    prob = native.Problem(name, horizon=horizon)
+    ora = _oracle.OracleProblem(name, horizon=horizon)
+    B, alpha, steps = 3, 0.5, 3
+    frames, refs = prob.sample_inputs(B, 0xB200 + 11)
+    s = prob.get_settings()
+    s.sqp_alpha, s.sqp_step_num = alpha, steps
+    prob.solver.update_settings(s)
+    x0 = np.tile(frames, (1, prob.horizon))
+    x = x0.copy(); f = np.zeros(B); st = np.zeros((B, native.NSTATS))
+    prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, f, st)
+    assert prob.solver.device_dims()["resident"] & 2      # direct block-tridiagonal kernel, not PCG
+    ora.set_schedule(steps, alpha)
+    ora.set_qp_settings(_oracle.settings_from_b200(s))
+    ox, of, ost = ora.solve_batch(frames, refs, x0=x0)
+    assert np.isfinite(ox).all()
+    assert np.array_equal(st[:, native.STAT["admm_iters"]], ost[:, 2])
+    assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
+    assert rel_err(x, ox) < REL_SOLUTION
+    assert np.allclose(f, of, rtol=1e-6, atol=1e-9)
