@@ -47,7 +47,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU (weak scaling)")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (weak scaling); default 4096 (quadrotor), 592 otherwise")
+    ap.add_argument("--workload", default="quadrotor", choices=sorted(WORKLOADS),
+                    help="quadrotor = the configuration the metric is quoted on (default); the others are BASELINE.json's "
+                         "larger shapes, not bench lines of record")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -55,9 +58,34 @@ def parse_args():
     return ap.parse_args()
 
 
+WORKLOADS = {
+    "quadrotor": ("quadrotor MPC nx=12 nu=4 H=20 dt=0.005, multiple shooting RK4", "BASELINE.json configs[2]", 20),
+    "cartpole": ("cart-pole swing-up nx=4 nu=1 H=200 dt=0.01, multiple shooting RK4", "BASELINE.json configs[4]", 200),
+    "centroidal": ("centroidal legged-robot MPC nx=24 nu=12 H=50 dt=0.01 with friction pyramids", "BASELINE.json configs[3]", 50),
+}
+
+
+def select_workload(args):
+    """The default is the configuration the metric is quoted on; --workload switches the module constants."""
+    global PROBLEM, METRIC
+    PROBLEM = args.workload
+    METRIC = f"batched OCP SQP solves/sec (H={WORKLOADS[PROBLEM][2]})"
+    if args.batch <= 0:
+        args.batch = 4096 if PROBLEM == "quadrotor" else 592
+
+
+def initial_iterate(frames, horizon):
+    """Cold iterate x = 0 for the quadrotor (as the reference starts); the other shapes start from the initial
+    frame held over the horizon (x = 0 makes the first cart-pole QP primal infeasible)."""
+    x0 = np.tile(frames, (1, horizon))
+    if PROBLEM == "quadrotor":
+        x0[:] = 0.0
+    return x0
+
+
 def workload_config(batch, n_gpus):
-    return {"workload": f"quadrotor MPC nx=12 nu=4 H=20 dt=0.005, multiple shooting RK4, {batch} random initial states per GPU "
-                        f"(BASELINE.json configs[2])",
+    desc, cfg, _ = WORKLOADS[PROBLEM]
+    return {"workload": f"{desc}, {batch} random initial states per GPU ({cfg})",
             "solve_method": "CUDA_SQP", "SQP_step": ALPHA, "ADMM_step": STEP_NUM, "eps_abs": 1e-3, "eps_rel": 1e-3,
             "admm_max_iter": 10000, "batch_per_gpu": batch, "parallelism": f"instances sharded over {n_gpus} GPU(s), no data-path collective",
             "l2": "flushed between timed steps (256 MiB write); per-step QP buffers (163 MB at B=4096) also exceed L2"}
@@ -72,10 +100,11 @@ def cpu_run(sample: int, threads: int, repeats: int = 1, warmup: int = 0, reuse_
     if reuse_symbolic:   # variant without the reference's per-step symbolic re-setup
         ora.set_schedule(STEP_NUM, ALPHA, reuse_symbolic=True)
     frames, refs = ora.sample_inputs(sample, SEED)
+    x0 = initial_iterate(frames, ora.horizon)
     times = []
     for it in range(warmup + repeats):
         t0 = time.perf_counter()
-        ora.solve_batch(frames, refs, nthreads=threads)
+        ora.solve_batch(frames, refs, x0=x0, nthreads=threads)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     return times
@@ -86,7 +115,7 @@ def reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample or max(64, 32 * threads)
+    sample = args.cpu_sample or (max(64, 32 * threads) if PROBLEM == "quadrotor" else 2 * threads)
     times = cpu_run(sample, threads, repeats=args.steps, warmup=args.warmup)
     total = sum(times)
     value = sample * args.steps / total
@@ -204,13 +233,15 @@ def b200_arm(args):
     d_frames = torch.from_numpy(frames_h).to(dev); d_p = torch.from_numpy(refs_h).to(dev)
     d_lbx = torch.from_numpy(prob.lbx).to(dev); d_ubx = torch.from_numpy(prob.ubx).to(dev)
     d_lbg = torch.from_numpy(prob.lbg).to(dev); d_ubg = torch.from_numpy(prob.ubg).to(dev)
+    x0_h = initial_iterate(frames_h, prob.horizon)
+    d_x0 = torch.from_numpy(x0_h).to(dev)
     d_x = torch.zeros(B, prob.N, **f64); d_f = torch.zeros(B, **f64); d_stats = torch.zeros(B, ocp.NSTATS, **f64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = {}
     stream = torch.cuda.current_stream()
 
     def device_step():
-        d_x.zero_()
+        d_x.copy_(d_x0)
         sol.solve_batch_device(B, d_frames.data_ptr(), d_p.data_ptr(), d_lbx.data_ptr(), d_ubx.data_ptr(),
                                d_lbg.data_ptr(), d_ubg.data_ptr(), d_x.data_ptr(), d_f.data_ptr(), d_stats.data_ptr(),
                                stream.cuda_stream)
@@ -283,7 +314,7 @@ def b200_arm(args):
     nx, nf_, nst = hp_x.numpy(), hp_f.numpy(), hp_st.numpy()
 
     def host_step():
-        nx[:] = 0.0
+        nx[:] = x0_h
         sol.solve_batch(hp_frames.numpy(), hp_refs.numpy(), prob.lbx, prob.ubx, prob.lbg, prob.ubg, nx, nf_, nst)
 
     for _ in range(2):
@@ -306,7 +337,7 @@ def b200_arm(args):
     if rank == 0 and args.latency_solves > 0:
         x1 = np.zeros((1, prob.N)); f1 = np.zeros(1)
         for i in range(args.latency_solves + 5):
-            x1[:] = 0.0
+            x1[:] = x0_h[i % B]
             t0 = time.perf_counter()
             sol.solve_batch(frames_h[i % B:i % B + 1], refs_h[i % B:i % B + 1], prob.lbx, prob.ubx, prob.lbg, prob.ubg, x1, f1)
             if i >= 5:
@@ -316,7 +347,7 @@ def b200_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_sample or max(64, 64 * threads)   # ~20 core-seconds of CPU work
+        sample = args.cpu_sample or (max(64, 64 * threads) if PROBLEM == "quadrotor" else 2 * threads)   # ~20 core-seconds
         t = cpu_run(sample, threads, repeats=1, warmup=0)[0]
         t1 = cpu_run(min(sample, 32), 1, repeats=1, warmup=0)[0] / min(sample, 32)
         tr = cpu_run(sample, threads, repeats=1, warmup=0, reuse_symbolic=True)[0]
@@ -353,6 +384,7 @@ def b200_arm(args):
 
 def main():
     args = parse_args()
+    select_workload(args)
     if args.impl == "reference":
         reference_arm(args)
     else:
