@@ -110,6 +110,20 @@ def cpu_run(sample: int, threads: int, repeats: int = 1, warmup: int = 0, reuse_
     return times
 
 
+def cpu_latency_p50(solves: int):
+    """p50 wall time of single-instance solves on one host thread (latency of the CPU path)."""
+    import _oracle
+    ora = _oracle.OracleProblem(PROBLEM, alpha=ALPHA, step_num=STEP_NUM)
+    frames, refs = ora.sample_inputs(solves, SEED)
+    x0 = initial_iterate(frames, ora.horizon)
+    ms = []
+    for i in range(solves):
+        t0 = time.perf_counter()
+        ora.solve_batch(frames[i:i + 1], refs[i:i + 1], x0=x0[i:i + 1], nthreads=1)
+        ms.append(1e3 * (time.perf_counter() - t0))
+    return {"p50_ms": float(np.median(ms)), "solves": solves}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -350,12 +364,14 @@ def b200_arm(args):
         sample = args.cpu_sample or (max(64, 64 * threads) if PROBLEM == "quadrotor" else 2 * threads)   # ~20 core-seconds
         t = cpu_run(sample, threads, repeats=1, warmup=0)[0]
         t1 = cpu_run(min(sample, 32), 1, repeats=1, warmup=0)[0] / min(sample, 32)
+        p50_1t = cpu_latency_p50(200 if PROBLEM == "quadrotor" else 8)
         tr = cpu_run(sample, threads, repeats=1, warmup=0, reuse_symbolic=True)[0]
         cpu = {"value": sample / t, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{sample} instances of the same workload (first of the {B}), one instance per host thread at a time, "
                          f"{t:.1f} s wall; single-thread {1e3 * t1:.1f} ms/solve; restated reference CPU path (cold OSQP "
                          f"set-up every SQP step), value_without_resetup keeps ordering + elimination tree between steps",
-               "single_thread_ms_per_solve": 1e3 * t1, "value_without_resetup": sample / tr}
+               "single_thread_ms_per_solve": 1e3 * t1, "single_thread_p50_ms": p50_1t["p50_ms"],
+               "single_thread_p50_solves": p50_1t["solves"], "value_without_resetup": sample / tr}
 
     if world > 1:
         dist.barrier()

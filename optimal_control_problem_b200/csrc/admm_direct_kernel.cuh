@@ -703,6 +703,7 @@ __device__ __forceinline__ bool exact_block_code(const PatternDev& P) {
 }
 
 // block-size dispatch (uniform across the CTA)
+template <int kPlace>
 __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work& W) {
   // exact-size code assumes the pitch tri_ld == bs + 2 (what the host sets for even block sizes)
   if (P.tri_bs == 16 && P.tri_ld == 18) tri_factor_twisted<16>(P, W);
@@ -715,13 +716,16 @@ __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work&
     __syncthreads();
   }
 }
+template <int kPlace>
 __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
   if (P.tri_bs == 16 && P.tri_ld == 18) tri_solve_twisted<16>(P, W);
   else if (P.tri_bs == 20 && P.tri_ld == 22) tri_solve_twisted<20>(P, W);
-  else if (W.ring_slots > 0) {
-    if (P.tri_bs == 36 && P.tri_ld == 38) tri_solve_stream<36>(P, W);
-    else if (P.tri_bs == 24 && P.tri_ld == 26) tri_solve_stream<24>(P, W);
-    else tri_solve_stream<0>(P, W);
+  else if (kPlace == PLACE_MIXED && W.ring_slots > 0) {   // only the mixed placement streams generic blocks
+    if constexpr (kPlace == PLACE_MIXED) {
+      if (P.tri_bs == 36 && P.tri_ld == 38) tri_solve_stream<36>(P, W);
+      else if (P.tri_bs == 24 && P.tri_ld == 26) tri_solve_stream<24>(P, W);
+      else tri_solve_stream<0>(P, W);
+    }
   }
   else tri_solve(P, W);
 }
@@ -729,6 +733,7 @@ __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& 
 // ---------------------------------------------------------------------------------------
 // one QP, solved by the whole CTA
 // ---------------------------------------------------------------------------------------
+template <int kPlace>
 __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settings& S, const SolveArgs& A,
                                       const Work& W, Reducer& R, int inst, QpResult& out) {
   const int tid = threadIdx.x, T = blockDim.x;
@@ -840,7 +845,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
   clk.lap(OCP_B200_PHASE_SCALE);
   tri_assemble(P, W, rv, sigma);
   clk.lap(OCP_B200_PHASE_KKT_ASSEMBLE);
-  factor_dispatch(P, W);
+  factor_dispatch<kPlace>(P, W);
   clk.lap(OCP_B200_PHASE_FACTOR);
 
   const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : 4 * S.check_termination;
@@ -856,7 +861,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
     }
     __syncthreads();
     clk.lap(OCP_B200_PHASE_RHS);
-    solve_dispatch(P, W);   // b <- x~
+    solve_dispatch<kPlace>(P, W);   // b <- x~
     ++solves;
     clk.lap(OCP_B200_PHASE_SOLVE);
 
@@ -1016,7 +1021,7 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
         rv = Rho(rho);
         for (int i = tid; i < m; i += T) W.w[i] = rv.of(W.ctype[i]) * W.z[i] - W.y[i];
         tri_assemble(P, W, rv, sigma);
-        factor_dispatch(P, W);
+        factor_dispatch<kPlace>(P, W);
       }
     }
     clk.lap(OCP_B200_PHASE_CHECK);
@@ -1077,7 +1082,7 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
     __syncthreads();
     if (inst >= A.B) break;
     QpResult res;
-    solve_instance(PL, S, A, W, R, inst, res);
+    solve_instance<kPlace>(PL, S, A, W, R, inst, res);
     write_outputs(P, A, W.x, W.y, R, inst, res);
   }
 }
