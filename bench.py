@@ -31,6 +31,9 @@ from pathlib import Path
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own banner / debug output (it prints to stdout) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
