@@ -31,8 +31,26 @@ from pathlib import Path
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own banner / debug output (it prints to stdout) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+# its version banner there), so fd 1 is pointed at stderr for the duration of the run and the line is written
+# to the saved descriptor.
+_RESULT_FD = None
+
+
+def capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -145,7 +163,7 @@ def reference_arm(args):
                                        "installable here), cold OSQP set-up every SQP step like the reference"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -396,7 +414,7 @@ def b200_arm(args):
                 "latency_p50_ms": float(np.median(lat)) if lat else None,
                 "solved_fraction": solved / B,
                 "device": torch.cuda.get_device_name(local), "kernel_plan": dict(dd, linsys="block-tridiagonal LDL' (direct)" if direct else "PCG")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -404,6 +422,7 @@ def b200_arm(args):
 def main():
     args = parse_args()
     select_workload(args)
+    capture_stdout()
     if args.impl == "reference":
         reference_arm(args)
     else:
