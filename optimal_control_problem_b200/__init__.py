@@ -152,6 +152,25 @@ def host_lib() -> C.CDLL:
         lib.ocp_host_compute_optimal_trajectory_batch.argtypes = [vptr, C.c_int, dptr, dptr, dptr, dptr, dptr]
         lib.ocp_host_problem_reset.argtypes = [vptr]
         lib.ocp_host_problem_shift_batch.argtypes = [vptr]
+        pv = C.POINTER(vptr)
+        lib.ocp_host_sx_sym.argtypes = [C.c_char_p, C.c_int, pv]
+        lib.ocp_host_sx_const.argtypes = [dptr, C.c_int, pv]
+        lib.ocp_host_sx_unary.argtypes = [C.c_char_p, vptr, pv]
+        lib.ocp_host_sx_binary.argtypes = [C.c_char_p, vptr, vptr, pv]
+        lib.ocp_host_sx_vertcat.argtypes = [pv, C.c_int, pv]
+        lib.ocp_host_sx_slice.argtypes = [vptr, C.c_int, C.c_int, pv]
+        lib.ocp_host_sx_size.argtypes = [vptr]
+        lib.ocp_host_sx_free.argtypes = [vptr]
+        lib.ocp_host_scripted_create.argtypes = [C.c_char_p, C.c_char_p, pv]
+        lib.ocp_host_scripted_info.argtypes = [vptr, iptr, dptr, iptr]
+        lib.ocp_host_scripted_variable.argtypes = [vptr, C.c_int, C.c_char_p, pv]
+        lib.ocp_host_scripted_set_reference.argtypes = [vptr, vptr]
+        lib.ocp_host_scripted_add_scalar_cost.argtypes = [vptr, vptr]
+        lib.ocp_host_scripted_add_vector_cost.argtypes = [vptr, dptr, C.c_int, vptr]
+        lib.ocp_host_scripted_add_inequality.argtypes = [vptr, C.c_char_p, dptr, vptr, dptr, C.c_int]
+        lib.ocp_host_scripted_add_equation.argtypes = [vptr, C.c_char_p, vptr, vptr]
+        lib.ocp_host_scripted_gen_solver.argtypes = [vptr]
+        lib.ocp_host_default_yaml.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_char_p, C.c_int]
         lib.ocp_host_sample_inputs.argtypes = [C.c_char_p, C.c_int, C.c_ulonglong, dptr, dptr]
         lib.ocp_host_kat_create.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(vptr)]
         lib.ocp_host_kat_destroy.argtypes = [vptr]
@@ -341,6 +360,18 @@ class Problem:
         else:
             _hcheck(lib.ocp_host_problem_create(name.encode(), horizon, alpha, step_num, C.byref(out)))
         self._h = out
+        self._load_description()
+
+    @classmethod
+    def _adopt(cls, name: str, handle) -> "Problem":
+        """Wraps a host problem that already went through genSolver() (symbolic.OptimalControlProblem)."""
+        self = cls.__new__(cls)
+        self.name, self._h = name, handle
+        self._load_description()
+        return self
+
+    def _load_description(self) -> None:
+        lib = host_lib()
         dims = (C.c_int * 8)()
         _hcheck(lib.ocp_host_problem_dims(self._h, dims))
         self.np_, self.nf, self.horizon, self.ng, self.n, self.m, self.nnz_h, self.nnz_a = list(dims)

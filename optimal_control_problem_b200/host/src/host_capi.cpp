@@ -4,6 +4,7 @@
 // CuCaQP); the numerical work happens behind include/ocp_b200.h on the GPU.
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 
@@ -26,6 +27,42 @@ struct HostNlp {  // a bare SQPOptimizationSolver over a test/test.cpp NLP
 };
 
 std::vector<double> dense(const casadi::DM& d) { return densify(d).nonzeros(); }
+
+void cache_bounds(HostProblem* hp) {
+  hp->lbx = dense(casadi::DM::vertcat(hp->ocp->OCPConfigPtr_->getLowerBounds()));
+  hp->ubx = dense(casadi::DM::vertcat(hp->ocp->OCPConfigPtr_->getUpperBounds()));
+  hp->lbg = dense(casadi::DM::vertcat(hp->ocp->getConstraintLowerBounds()));
+  hp->ubg = dense(casadi::DM::vertcat(hp->ocp->getConstraintUpperBounds()));
+}
+
+// An OptimalControlProblem whose costs and constraints are registered from outside (the Python
+// front-end of optimal_control_problem_b200/symbolic.py) instead of in an overridden
+// deployConstraintsAndAddCost(): what the reference's pybind trampoline class would have done
+// (src/pybind/python_bindings.cpp:380-445, commented out upstream).
+class ScriptedOCP : public OptimalControlProblem {
+ public:
+  ScriptedOCP(YAML::Node node, const std::string& name) : OptimalControlProblem(node) { setProblemName(name); }
+  void deployConstraintsAndAddCost() override {}
+};
+
+int op_code(const std::string& op, bool binary) {
+  static const std::map<std::string, int> bin = {{"add", casadi::OP_ADD}, {"sub", casadi::OP_SUB}, {"mul", casadi::OP_MUL},
+      {"div", casadi::OP_DIV}, {"pow", casadi::OP_POW}, {"atan2", casadi::OP_ATAN2}, {"fmin", casadi::OP_FMIN},
+      {"fmax", casadi::OP_FMAX}};
+  static const std::map<std::string, int> un = {{"neg", casadi::OP_NEG}, {"sq", casadi::OP_SQ}, {"sqrt", casadi::OP_SQRT},
+      {"sin", casadi::OP_SIN}, {"cos", casadi::OP_COS}, {"tan", casadi::OP_TAN}, {"asin", casadi::OP_ASIN},
+      {"acos", casadi::OP_ACOS}, {"atan", casadi::OP_ATAN}, {"exp", casadi::OP_EXP}, {"log", casadi::OP_LOG},
+      {"fabs", casadi::OP_FABS}, {"sign", casadi::OP_SIGN}, {"tanh", casadi::OP_TANH}, {"sinh", casadi::OP_SINH},
+      {"cosh", casadi::OP_COSH}};
+  const auto& m = binary ? bin : un;
+  auto it = m.find(op);
+  if (it == m.end()) throw std::invalid_argument("unknown SX operation: " + op);
+  return it->second;
+}
+casadi::SX& sx(void* h) {
+  if (!h) throw std::invalid_argument("SX handle is NULL");
+  return *static_cast<casadi::SX*>(h);
+}
 }  // namespace
 
 #define HOST_TRY try {
@@ -66,6 +103,110 @@ int ocp_host_problem_create_yaml(const char* name, const char* yaml_text, void**
   hp->lbg = dense(casadi::DM::vertcat(hp->ocp->getConstraintLowerBounds()));
   hp->ubg = dense(casadi::DM::vertcat(hp->ocp->getConstraintUpperBounds()));
   *out = hp.release();
+  HOST_CATCH
+}
+
+// ---- symbolic expressions for the Python front-end: opaque casadi::SX handles ------------------------
+int ocp_host_sx_sym(const char* name, int n, void** out) {
+  HOST_TRY
+  *out = new casadi::SX(casadi::SX::sym(name, n));
+  HOST_CATCH
+}
+int ocp_host_sx_const(const double* v, int n, void** out) {
+  HOST_TRY
+  *out = new casadi::SX(std::vector<double>(v, v + n));
+  HOST_CATCH
+}
+int ocp_host_sx_unary(const char* op, void* a, void** out) {
+  HOST_TRY
+  *out = new casadi::SX(casadi::SX::unary(op_code(op, false), sx(a)));
+  HOST_CATCH
+}
+int ocp_host_sx_binary(const char* op, void* a, void* b, void** out) {
+  HOST_TRY
+  *out = new casadi::SX(casadi::SX::binary(op_code(op, true), sx(a), sx(b)));
+  HOST_CATCH
+}
+int ocp_host_sx_vertcat(void** parts, int count, void** out) {
+  HOST_TRY
+  std::vector<casadi::SX> v;
+  for (int i = 0; i < count; ++i) v.push_back(sx(parts[i]));
+  *out = new casadi::SX(casadi::SX::vertcat(v));
+  HOST_CATCH
+}
+int ocp_host_sx_slice(void* a, int start, int stop, void** out) {
+  HOST_TRY
+  const casadi::SX& x = sx(a);
+  if (start < 0 || stop > x.size1() || start > stop) throw std::out_of_range("SX slice out of range");
+  *out = new casadi::SX(x(casadi::Slice(start, stop)));
+  HOST_CATCH
+}
+int ocp_host_sx_size(void* a) { return a ? static_cast<int>(static_cast<casadi::SX*>(a)->size1()) : -1; }
+int ocp_host_sx_free(void* a) { delete static_cast<casadi::SX*>(a); return 0; }
+
+// ---- an OptimalControlProblem assembled call by call (see ScriptedOCP) --------------------------------
+int ocp_host_scripted_create(const char* name, const char* yaml_text, void** out) {
+  HOST_TRY
+  YAML::Node node = YAML::Load(yaml_text);
+  if (node["optimal_control_problem"]) node = node["optimal_control_problem"];
+  auto hp = std::make_unique<HostProblem>();
+  hp->name = name;
+  hp->ocp = std::make_unique<ScriptedOCP>(node, name);
+  *out = hp.release();
+  HOST_CATCH
+}
+int ocp_host_scripted_info(void* h, int* horizon, double* dt, int* frame_size) {
+  HOST_TRY
+  auto& cfg = *static_cast<HostProblem*>(h)->ocp->OCPConfigPtr_;
+  *horizon = cfg.getHorizon(); *dt = cfg.getDt(); *frame_size = cfg.getFrameSize();
+  HOST_CATCH
+}
+int ocp_host_scripted_variable(void* h, int k, const char* field, void** out) {
+  HOST_TRY
+  *out = new casadi::SX(static_cast<HostProblem*>(h)->ocp->OCPConfigPtr_->getVariable(k, field));
+  HOST_CATCH
+}
+int ocp_host_scripted_set_reference(void* h, void* ref) {
+  HOST_TRY
+  static_cast<HostProblem*>(h)->ocp->setReference(sx(ref));
+  HOST_CATCH
+}
+int ocp_host_scripted_add_scalar_cost(void* h, void* cost) {
+  HOST_TRY
+  static_cast<HostProblem*>(h)->ocp->addScalarCost(sx(cost));
+  HOST_CATCH
+}
+int ocp_host_scripted_add_vector_cost(void* h, const double* w, int n, void* cost) {
+  HOST_TRY
+  static_cast<HostProblem*>(h)->ocp->addVectorCost(std::vector<double>(w, w + n), sx(cost));
+  HOST_CATCH
+}
+int ocp_host_scripted_add_inequality(void* h, const char* name, const double* lb, void* expr, const double* ub, int n) {
+  HOST_TRY
+  static_cast<HostProblem*>(h)->ocp->addInequalityConstraint(name, casadi::DM(std::vector<double>(lb, lb + n)), sx(expr),
+                                                             casadi::DM(std::vector<double>(ub, ub + n)));
+  HOST_CATCH
+}
+int ocp_host_scripted_add_equation(void* h, const char* name, void* lhs, void* rhs) {
+  HOST_TRY
+  if (rhs) static_cast<HostProblem*>(h)->ocp->addEquationConstraint(name, sx(lhs), sx(rhs));
+  else static_cast<HostProblem*>(h)->ocp->addEquationConstraint(name, sx(lhs));
+  HOST_CATCH
+}
+// genSolver(): symbolic AD, stage code generation, nvcc -- no GPU needed
+int ocp_host_scripted_gen_solver(void* h) {
+  HOST_TRY
+  HostProblem* hp = static_cast<HostProblem*>(h);
+  hp->ocp->genSolver();
+  cache_bounds(hp);
+  HOST_CATCH
+}
+// YAML text of the built-in benchmark problems (so that a scripted problem can share their settings)
+int ocp_host_default_yaml(const char* name, int horizon, double alpha, int step_num, char* buf, int cap) {
+  HOST_TRY
+  const std::string y = ocp_problems::default_yaml(name, horizon, alpha, step_num, false);
+  if (static_cast<int>(y.size()) + 1 > cap) throw std::length_error("default_yaml: buffer too small");
+  std::memcpy(buf, y.c_str(), y.size() + 1);
   HOST_CATCH
 }
 
