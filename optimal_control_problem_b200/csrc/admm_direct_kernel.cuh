@@ -491,15 +491,36 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int np = P.tri_np, nb = P.tri_nb;
   const int bs = kBS > 0 ? kBS : P.tri_bs, ld = kBS > 0 ? kBS + 2 : P.tri_ld, N = nb * bs;
-  double* bx = W.b + np;
+  // fields are copied into locals: W and P live in the caller's frame and the "memory" clobbers of the
+  // barrier / bulk-copy instructions would turn each later use into a reload through local memory
+  double* const wb = W.b;
+  double* const bx = wb + np;
+  const double* const Lsub = W.Lsub;
+  const double* const Dinv = W.Dinv;
+  const double* const Lp = W.Lp;
+  double* const xp = W.xp;
+  const double* const Dp = W.Dp;
+  double* const Dp2 = W.Dp2;
+  double* const stage = W.stage;
+  double* const Sbuf = W.S;
+  unsigned long long* const ring_bar = W.ring_bar;
+  unsigned* const ring_phase = W.ring_phase;
+  const int s_stride = W.s_stride, stage_slots = P.stage_slots;
   const int R = W.ring_slots, stride = W.stage_stride;
   const uint32_t bytes = static_cast<uint32_t>(bs * ld * sizeof(double));
   const int nthr = ((4 * bs + 31) / 32) * 32;   // participating threads (whole warps)
   const int row = tid >> 2, sub = tid & 3;
   const bool part = tid < nthr, act = part && row < bs;
+  // the warp after the compute warps only issues the bulk copies (an issue costs the issuing warp ~300
+  // cycles, which would otherwise sit on the critical path of every stage); it joins the named barrier of
+  // the stages, so it knows when a slot is free.  Without a spare warp thread 0 issues.
+  const bool has_issuer = nthr + 32 <= T;
+  const bool issue_thread = has_issuer ? tid == nthr : tid == 0;
+  const bool in_loop = part || (has_issuer && tid < nthr + 32);
+  const int nbar = has_issuer ? nthr + 32 : nthr;
   const int rr = act ? row : 0;
   constexpr int kPer = kBS > 0 ? (kBS + 3) / 4 : 16;   // columns per lane (bs <= 64)
-  uint32_t ph = W.ring_phase[0];   // identical in every participating thread
+  uint32_t ph = ring_phase[0];   // identical in every participating thread
   OCP_B200_FINE_CLOCK(clk, W.phase);
 
   // The three block phases form ONE stream of G = 2 (nb - 1) + nb blocks, so the ring never drains
@@ -508,20 +529,20 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   const int G = 2 * (nb - 1) + nb;
   const size_t blk_doubles = size_t(bs) * ld;
   auto gaddr = [&](int g) -> const double* {
-    if (g < nb - 1) return W.Lsub + size_t(1 + g) * blk_doubles;
+    if (g < nb - 1) return Lsub + size_t(1 + g) * blk_doubles;
     g -= nb - 1;
-    if (g < nb) return W.Dinv + size_t(g) * blk_doubles;
+    if (g < nb) return Dinv + size_t(g) * blk_doubles;
     g -= nb;
-    return W.Lsub + size_t(nb - 1 - g) * blk_doubles;
+    return Lsub + size_t(nb - 1 - g) * blk_doubles;
   };
   auto slot_ptr = [&](int sl) -> double* {
-    return sl < P.stage_slots ? W.stage + sl * stride : W.S + (sl - P.stage_slots) * W.s_stride;
+    return sl < stage_slots ? stage + sl * stride : Sbuf + (sl - stage_slots) * s_stride;
   };
-  if (tid == 0)
-    for (int i = 0; i < R && i < G; ++i) ring_issue(slot_ptr(i), gaddr(i), bytes, W.ring_bar + i);
+  if (issue_thread)
+    for (int i = 0; i < R && i < G; ++i) ring_issue(slot_ptr(i), gaddr(i), bytes, ring_bar + i);
   int g = 0, s = 0;   // stream position, ring slot
   auto advance = [&]() {   // after the stage's barrier: the slot is free, request the block R positions ahead
-    if (tid == 0 && g + R < G) ring_issue(slot_ptr(s), gaddr(g + R), bytes, W.ring_bar + s);
+    if (issue_thread && g + R < G) ring_issue(slot_ptr(s), gaddr(g + R), bytes, ring_bar + s);
     ++g;
     s = s + 1 == R ? 0 : s + 1;
   };
@@ -552,14 +573,16 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   };
 
   // forward sweep: y_k = b_k - L_k y_{k-1}, k = 1..nb-1
-  if (part) {
+  if (in_loop) {
     for (int t = 0; t < nb - 1; ++t) {
-      ring_wait(W.ring_bar + s, (ph >> s) & 1u);
-      ph ^= 1u << s;
-      const double old = (act && sub == 0) ? bx[(t + 1) * bs + row] : 0.0;
-      const double sum = block_dot(slot_ptr(s), bx + t * bs, false);
-      if (act && sub == 0) bx[(t + 1) * bs + row] = old - sum;
-      asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
+      if (part) {
+        ring_wait(ring_bar + s, (ph >> s) & 1u);
+        ph ^= 1u << s;
+        const double old = (act && sub == 0) ? bx[(t + 1) * bs + row] : 0.0;
+        const double sum = block_dot(slot_ptr(s), bx + t * bs, false);
+        if (act && sub == 0) bx[(t + 1) * bs + row] = old - sum;
+      }
+      asm volatile("bar.sync 4, %0;" ::"r"(nbar) : "memory");
       advance();
     }
   }
@@ -571,18 +594,18 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   // issued together; the warps' sums meet in shared memory in a fixed order.  Then x_p = D_p^-1 y_p.
   if (np > 0) {
     const bool vec = (N & 1) == 0 && (reinterpret_cast<unsigned long long>(bx) & 15ULL) == 0ULL &&
-                     (reinterpret_cast<unsigned long long>(W.Lp) & 15ULL) == 0ULL;
-    double* part_sums = W.Dp2;   // factor scratch, free during a solve: [warp][8]
+                     (reinterpret_cast<unsigned long long>(Lp) & 15ULL) == 0ULL;
+    double* part_sums = Dp2;   // factor scratch, free during a solve: [warp][8]
     const bool wide_border = 2 * np * (np + 1) >= nw * 8;
     if (!wide_border) {   // small border: a warp per row
       for (int r = warp; r < np; r += nw) {
         double sacc = 0.0;
-        const double* rowp = W.Lp + size_t(r) * N;
+        const double* rowp = Lp + size_t(r) * N;
 #pragma unroll 8
         for (int j = lane; j < N; j += 32) sacc += rowp[j] * bx[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-        if (lane == 0) W.xp[r] = W.b[r] - sacc;
+        if (lane == 0) xp[r] = wb[r] - sacc;
       }
       __syncthreads();
     }
@@ -595,7 +618,7 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
           double2 v[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            v[q] = r0 + q < np ? reinterpret_cast<const double2*>(W.Lp + size_t(r0 + q) * N)[j] : make_double2(0.0, 0.0);
+            v[q] = r0 + q < np ? reinterpret_cast<const double2*>(Lp + size_t(r0 + q) * N)[j] : make_double2(0.0, 0.0);
           const double2 y = y2[j];
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[q] = fma(v[q].x, y.x, fma(v[q].y, y.y, acc[q]));
@@ -605,7 +628,7 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
           const double y = bx[j];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (r0 + q < np) acc[q] = fma(W.Lp[size_t(r0 + q) * N + j], y, acc[q]);
+            if (r0 + q < np) acc[q] = fma(Lp[size_t(r0 + q) * N + j], y, acc[q]);
         }
       }
 #pragma unroll
@@ -618,14 +641,14 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
       if (tid < 8 && r0 + tid < np) {
         double sacc = 0.0;
         for (int w = 0; w < nw; ++w) sacc += part_sums[w * 8 + tid];
-        W.xp[r0 + tid] = W.b[r0 + tid] - sacc;
+        xp[r0 + tid] = wb[r0 + tid] - sacc;
       }
       __syncthreads();
     }
     if (tid < np) {
       double sacc = 0.0;
-      for (int c = 0; c < np; ++c) sacc += W.Dp[tid * (np + 1) + c] * W.xp[c];
-      W.b[tid] = sacc;
+      for (int c = 0; c < np; ++c) sacc += Dp[tid * (np + 1) + c] * xp[c];
+      wb[tid] = sacc;
     }
     __syncthreads();
   }
@@ -633,7 +656,7 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
 
   // diagonal phase: c_k = D_k^-1 y_k - L_pk' x_p, block by block through the ring; the L_p values of
   // the next block are requested before the current block is multiplied
-  if (part) {
+  if (in_loop) {
     const int count = nb;
     constexpr int kMaxLp = 8;   // border rows per lane: np <= 32
     const bool lp_regs = np <= 4 * kMaxLp;
@@ -642,13 +665,13 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
 #pragma unroll
       for (int i = 0; i < kMaxLp; ++i) {
         const int p = sub + 4 * i;
-        lpn[i] = (act && p < np) ? W.Lp[size_t(p) * N + k * bs + row] : 0.0;
+        lpn[i] = (act && p < np) ? Lp[size_t(p) * N + k * bs + row] : 0.0;
       }
     };
     if (lp_regs) fetch_lp(0);
     double xpv[kMaxLp];
 #pragma unroll
-    for (int i = 0; i < kMaxLp; ++i) xpv[i] = (lp_regs && sub + 4 * i < np) ? W.b[sub + 4 * i] : 0.0;
+    for (int i = 0; i < kMaxLp; ++i) xpv[i] = (lp_regs && sub + 4 * i < np) ? wb[sub + 4 * i] : 0.0;
     for (int k = 0; k < count; ++k) {
       double corr = 0.0, corr1 = 0.0;
       if (lp_regs) {
@@ -657,14 +680,17 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
         corr += corr1;
         if (k + 1 < count) fetch_lp(k + 1);
       } else if (act) {
-        for (int p = sub; p < np; p += 4) corr = fma(W.Lp[size_t(p) * N + k * bs + row], W.b[p], corr);
+        for (int p = sub; p < np; p += 4) corr = fma(Lp[size_t(p) * N + k * bs + row], wb[p], corr);
       }
-      ring_wait(W.ring_bar + s, (ph >> s) & 1u);
-      ph ^= 1u << s;
-      double v = block_dot(slot_ptr(s), bx + k * bs, false);
-      corr += __shfl_xor_sync(0xffffffffu, corr, 1);
-      corr += __shfl_xor_sync(0xffffffffu, corr, 2);
-      asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");   // every row has read y_k
+      double v = 0.0;
+      if (part) {
+        ring_wait(ring_bar + s, (ph >> s) & 1u);
+        ph ^= 1u << s;
+        v = block_dot(slot_ptr(s), bx + k * bs, false);
+        corr += __shfl_xor_sync(0xffffffffu, corr, 1);
+        corr += __shfl_xor_sync(0xffffffffu, corr, 2);
+      }
+      asm volatile("bar.sync 4, %0;" ::"r"(nbar) : "memory");   // every row has read y_k
       if (act && sub == 0) bx[k * bs + row] = v - corr;
       advance();
     }
@@ -673,19 +699,245 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
 
   // backward sweep: x_k = c_k - L_{k+1}' x_{k+1}, k = nb-2..0
-  if (part) {
+  if (in_loop) {
     for (int t = 0; t < nb - 1; ++t) {
       const int blkid = nb - 1 - t;
-      ring_wait(W.ring_bar + s, (ph >> s) & 1u);
-      ph ^= 1u << s;
-      const double old = (act && sub == 0) ? bx[(blkid - 1) * bs + row] : 0.0;
-      const double sum = block_dot(slot_ptr(s), bx + blkid * bs, true);
-      if (act && sub == 0) bx[(blkid - 1) * bs + row] = old - sum;
-      asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory");
+      if (part) {
+        ring_wait(ring_bar + s, (ph >> s) & 1u);
+        ph ^= 1u << s;
+        const double old = (act && sub == 0) ? bx[(blkid - 1) * bs + row] : 0.0;
+        const double sum = block_dot(slot_ptr(s), bx + blkid * bs, true);
+        if (act && sub == 0) bx[(blkid - 1) * bs + row] = old - sum;
+      }
+      asm volatile("bar.sync 4, %0;" ::"r"(nbar) : "memory");
       advance();
     }
   }
-  if (tid == 0) W.ring_phase[0] = ph;
+  if (tid == 0) ring_phase[0] = ph;
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
+}
+
+// Streamed solve against the TWISTED factor of tri_twisted.cuh (blocks eliminated from both ends, meeting
+// at block mid = nb / 2): two thread groups, four lanes per block row each, run the two chains of the
+// forward sweep, split the diagonal phase between them and run the two chains of the backward sweep; each
+// group pulls ITS sequence of factor blocks through its own ring (half of the staging area), as one stream
+// that keeps filling across the phases and during the border product.  Used when the factor is slab-resident
+// and a block row is too long for one lane (tri_twisted.cuh: one warp per chain, one lane per row, costs
+// ~900 cycles per stage for 20 columns; this form ~300).
+template <int kBS>
+__device__ __noinline__ void tri_solve_stream_twisted(const PatternDev& P, const Work& W) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  // every field used below is copied into a local first: W and P live in the caller's frame, and the
+  // "memory" clobbers of the barrier / bulk-copy instructions would make each later use a reload
+  // through local memory (an L2 round trip when shared memory leaves almost no L1)
+  const int np = P.tri_np, nb = P.tri_nb;
+  constexpr int bs = kBS, ld = kBS + 2;
+  const int N = nb * bs, mid = nb / 2;
+  double* const wb = W.b;
+  double* const bx = wb + np;
+  const double* const Lsub = W.Lsub;
+  const double* const Dinv = W.Dinv;
+  const double* const Lp = W.Lp;
+  double* const xp = W.xp;
+  double* const piv = W.piv;
+  const double* const Dp = W.Dp;
+  unsigned* const ring_phase = W.ring_phase;
+  const int R = W.ring_slots, stride = W.stage_stride;
+  constexpr uint32_t bytes = bs * ld * sizeof(double);
+  constexpr int nthr = ((4 * bs + 31) / 32) * 32;   // threads per group (whole warps)
+  const int GT = T / 2, grp = tid >= GT ? 1 : 0, gt = tid - grp * GT;
+  const int row = gt >> 2, sub = gt & 3;
+  // the warp after a group's compute warps only issues the bulk copies: an issue costs the issuing warp
+  // ~300 cycles, which would otherwise sit on the critical path of every stage; it joins the group's
+  // named barrier, so it knows when a slot is free
+  const bool part = gt < nthr, act = part && row < bs;
+  const bool issuer = gt >= nthr && gt < nthr + 32, in_grp = part || issuer;
+  constexpr int nbar = nthr + 32;
+  const int rr = act ? row : 0;
+  constexpr int kPer = (kBS + 3) / 4;
+  uint32_t ph = ring_phase[grp];
+  double* ring = W.stage + grp * R * stride;
+  unsigned long long* bars = W.ring_bar + grp * kMaxRing;
+  const int bar_id = 1 + grp;
+  OCP_B200_FINE_CLOCK(clk, W.phase);
+
+  // this group's block sequence: forward chain, (group 0: the two joining blocks,) its share of the
+  // diagonal phase, backward chain
+  const int n_fwd = grp == 0 ? mid - 1 : nb - 2 - mid;
+  const int n_join = grp == 0 ? 2 : 0;
+  const int n_diag = grp == 0 ? mid + 1 : nb - 1 - mid;
+  const int n_bwd = grp == 0 ? mid : nb - 1 - mid;
+  const int G = n_fwd + n_join + n_diag + n_bwd;
+  constexpr size_t blk_doubles = size_t(bs) * ld;
+  auto gaddr = [&](int g) -> const double* {
+    if (g < n_fwd) return Lsub + size_t(grp == 0 ? 1 + g : nb - 1 - g) * blk_doubles;
+    g -= n_fwd;
+    if (g < n_join) return Lsub + size_t(mid + g) * blk_doubles;
+    g -= n_join;
+    if (g < n_diag) return Dinv + size_t(grp == 0 ? g : mid + 1 + g) * blk_doubles;
+    g -= n_diag;
+    return Lsub + size_t(grp == 0 ? mid - g : mid + 1 + g) * blk_doubles;
+  };
+  if (issuer && lane == 0)
+    for (int i = 0; i < R && i < G; ++i) ring_issue(ring + i * stride, gaddr(i), bytes, bars + i);
+  int g = 0, s = 0;
+  auto advance = [&]() {
+    if (issuer && lane == 0 && g + R < G) ring_issue(ring + s * stride, gaddr(g + R), bytes, bars + s);
+    ++g;
+    s = s + 1 == R ? 0 : s + 1;
+  };
+  auto block_dot = [&](const double* blk, const double* src, bool column) {
+    double mv[kPer], sv[kPer];
+    const double* mp = column ? blk + rr : blk + rr * ld;
+    const int ms = column ? ld : 1;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int c = sub + 4 * i;
+      const bool ok = c < bs;
+      mv[i] = ok ? mp[c * ms] : 0.0;
+      sv[i] = ok ? src[c] : 0.0;
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPer; i += 2) {
+      s0 = fma(mv[i], sv[i], s0);
+      if (i + 1 < kPer) s1 = fma(mv[i + 1], sv[i + 1], s1);
+    }
+    double sum = s0 + s1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    return sum;
+  };
+  // one sweep stage: dst block -= M src block (M row-wise in the forward sweeps, transposed in the backward ones)
+  auto sweep = [&](int dstb, int srcb, bool column) {
+    if (part) {
+      ring_wait(bars + s, (ph >> s) & 1u);
+      ph ^= 1u << s;
+      const double old = (act && sub == 0) ? bx[dstb * bs + row] : 0.0;
+      const double sum = block_dot(ring + s * stride, bx + srcb * bs, column);
+      if (act && sub == 0) bx[dstb * bs + row] = old - sum;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nbar) : "memory");
+    advance();
+  };
+
+  // forward: top chain y_k = b_k - L_k y_{k-1} (k = 1..mid-1), bottom chain y_k = b_k - U_k y_{k+1} (k = nb-2..mid+1)
+  if (in_grp) {
+    if (grp == 0) for (int i = 0; i < n_fwd; ++i) sweep(1 + i, i, false);
+    else for (int i = 0; i < n_fwd; ++i) sweep(nb - 2 - i, nb - 1 - i, false);
+  }
+  __syncthreads();
+  if (in_grp && grp == 0) {   // both contributions to block mid
+    sweep(mid, mid - 1, false);
+    sweep(mid, mid + 1, false);
+  }
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
+
+  // border: y_p = b_p - sum_k L_pk y_k with TPR threads per border row (one or two batches of eight
+  // loads each, so a slab-resident L_p costs one or two round trips), then x_p = D_p^-1 y_p
+  if (np > 0) {
+    int TPR = 32;
+    while (TPR * 2 * np <= T && (TPR * 2 / 32) * np <= 64 && TPR < 256) TPR *= 2;
+    const int wpr = TPR / 32;
+    if (np * 32 <= T) {
+      const int r = tid / TPR, q = tid - r * TPR;
+      const bool have = r < np;
+      const double* rowp = Lp + size_t(have ? r : 0) * N;
+      double s0 = 0.0, s1 = 0.0;
+      for (int j0 = q; j0 < N; j0 += 8 * TPR) {
+        double lv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + TPR * u;
+          const bool ok = have && j < N;
+          lv[u] = ok ? rowp[j] : 0.0;
+          yv[u] = ok ? bx[j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) { s0 = fma(lv[u], yv[u], s0); s1 = fma(lv[u + 1], yv[u + 1], s1); }
+      }
+      double sacc = s0 + s1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (have && lane == 0) piv[warp] = sacc;   // warp = r * wpr + (warp within the row)
+      __syncthreads();
+      if (tid < np) {
+        double t = 0.0;
+        for (int w = 0; w < wpr; ++w) t += piv[tid * wpr + w];
+        xp[tid] = wb[tid] - t;
+      }
+    } else {
+      const int nw = T >> 5;
+      for (int r = warp; r < np; r += nw) {
+        double sacc = 0.0;
+        const double* rowp = Lp + size_t(r) * N;
+#pragma unroll 8
+        for (int j = lane; j < N; j += 32) sacc += rowp[j] * bx[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) xp[r] = wb[r] - sacc;
+      }
+    }
+    __syncthreads();
+    if (tid < np) {
+      double sacc = 0.0;
+      for (int c = 0; c < np; ++c) sacc += Dp[tid * (np + 1) + c] * xp[c];
+      wb[tid] = sacc;
+    }
+    __syncthreads();
+  }
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
+
+  // diagonal phase, split between the groups: c_k = D_k^-1 y_k - L_pk' x_p
+  if (in_grp) {
+    const int k0 = grp == 0 ? 0 : mid + 1;
+    constexpr int kMaxLp = 4;   // border rows per lane: np <= 16, else read in place
+    const bool lp_regs = np <= 4 * kMaxLp;
+    double lpn[kMaxLp] = {0.0, 0.0, 0.0, 0.0}, xpv[kMaxLp];
+    auto fetch_lp = [&](int k) {
+#pragma unroll
+      for (int i = 0; i < kMaxLp; ++i) {
+        const int p = sub + 4 * i;
+        lpn[i] = (act && p < np) ? Lp[size_t(p) * N + k * bs + row] : 0.0;
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < kMaxLp; ++i) xpv[i] = (lp_regs && sub + 4 * i < np) ? wb[sub + 4 * i] : 0.0;
+    if (lp_regs && n_diag > 0) fetch_lp(k0);
+    for (int j = 0; j < n_diag; ++j) {
+      const int k = k0 + j;
+      double corr = 0.0;
+      if (lp_regs) {
+#pragma unroll
+        for (int i = 0; i < kMaxLp; ++i) corr = fma(lpn[i], xpv[i], corr);
+        if (j + 1 < n_diag) fetch_lp(k + 1);
+      } else if (act) {
+        for (int p = sub; p < np; p += 4) corr = fma(Lp[size_t(p) * N + k * bs + row], wb[p], corr);
+      }
+      double v = 0.0;
+      if (part) {
+        ring_wait(bars + s, (ph >> s) & 1u);
+        ph ^= 1u << s;
+        v = block_dot(ring + s * stride, bx + k * bs, false);
+        corr += __shfl_xor_sync(0xffffffffu, corr, 1);
+        corr += __shfl_xor_sync(0xffffffffu, corr, 2);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nbar) : "memory");   // every row has read y_k
+      if (act && sub == 0) bx[k * bs + row] = v - corr;
+      advance();
+    }
+  }
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
+
+  // backward, from block mid outwards: x_k = c_k - L_{k+1}' x_{k+1} (k = mid-1..0), x_k = c_k - U_{k-1}' x_{k-1} (k = mid+1..nb-1)
+  if (in_grp) {
+    if (grp == 0) for (int j = 0; j < n_bwd; ++j) sweep(mid - 1 - j, mid - j, true);
+    else for (int j = 0; j < n_bwd; ++j) sweep(mid + 1 + j, mid + j, true);
+  }
+  if (part && gt == 0) ring_phase[grp] = ph;
   __syncthreads();
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
 }
@@ -719,7 +971,13 @@ __device__ __forceinline__ void factor_dispatch(const PatternDev& P, const Work&
 template <int kPlace>
 __device__ __forceinline__ void solve_dispatch(const PatternDev& P, const Work& W) {
   if (P.tri_bs == 16 && P.tri_ld == 18) tri_solve_twisted<16>(P, W);
-  else if (P.tri_bs == 20 && P.tri_ld == 22) tri_solve_twisted<20>(P, W);
+  else if (P.tri_bs == 20 && P.tri_ld == 22) {
+    if (kPlace == PLACE_BIG && W.ring_slots >= 2 && P.tri_nb >= 4 && 2 * (((4 * 20 + 31) / 32) * 32 + 32) <= int(blockDim.x)) {
+      if constexpr (kPlace == PLACE_BIG) tri_solve_stream_twisted<20>(P, W);
+    } else {
+      tri_solve_twisted<20>(P, W);
+    }
+  }
   else if (kPlace == PLACE_MIXED && W.ring_slots > 0) {   // only the mixed placement streams generic blocks
     if constexpr (kPlace == PLACE_MIXED) {
       if (P.tri_bs == 36 && P.tri_ld == 38) tri_solve_stream<36>(P, W);
