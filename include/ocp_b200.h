@@ -232,6 +232,27 @@ int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int r
 int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int* nnz_a,
                       int* smem_bytes, int* resident);
 
+/* launch plan and linear-system structure of a handle (diagnostics, roofline accounting): fills up to
+ * `count` ints of v in the order of the OCP_B200_PLAN_* slots */
+#define OCP_B200_PLAN_WIDE_PLACE      0   /* throughput plan: placement id (0 mixed, 1 all shared, 2 multi-CTA, 3 big) */
+#define OCP_B200_PLAN_WIDE_THREADS    1
+#define OCP_B200_PLAN_WIDE_SMEM       2   /* dynamic shared memory bytes per CTA */
+#define OCP_B200_PLAN_WIDE_CTAS_SM    3   /* resident CTAs per SM */
+#define OCP_B200_PLAN_WIDE_SLAB_KB    4   /* per-CTA global slab, KiB */
+#define OCP_B200_PLAN_DEEP_PLACE      5   /* latency plan (batches of at most one instance per SM) */
+#define OCP_B200_PLAN_DEEP_THREADS    6
+#define OCP_B200_PLAN_DEEP_SMEM       7
+#define OCP_B200_PLAN_DEEP_CTAS_SM    8
+#define OCP_B200_PLAN_DEEP_SLAB_KB    9
+#define OCP_B200_PLAN_TRI_OK         10   /* 1: K is bordered block tridiagonal and the direct kernel is used */
+#define OCP_B200_PLAN_TRI_NP         11   /* border columns */
+#define OCP_B200_PLAN_TRI_BS         12   /* block size */
+#define OCP_B200_PLAN_TRI_NB         13   /* number of diagonal blocks */
+#define OCP_B200_PLAN_NNZ_P          14   /* entries of the symmetrised upper triangle of H */
+#define OCP_B200_PLAN_NUM_SMS        15
+#define OCP_B200_PLAN_COUNT          16
+int ocp_b200_get_plan(const ocp_b200_solver* s, int* v, int count);
+
 const char* ocp_b200_last_error(void);
 int ocp_b200_abi_version(void);
 

@@ -117,6 +117,7 @@ def cuda_lib() -> C.CDLL:
         lib.ocp_b200_qp_solve_batch.argtypes = [vptr, C.c_int] + [dptr] * 8
         lib.ocp_b200_admm_trace.argtypes = [vptr] + [dptr] * 5 + [C.c_int, dptr, C.POINTER(C.c_int), dptr, dptr]
         lib.ocp_b200_get_dims.argtypes = [vptr] + [C.POINTER(C.c_int)] * 6
+        lib.ocp_b200_get_plan.argtypes = [vptr, C.POINTER(C.c_int), C.c_int]
         lib.ocp_b200_set_profiling.argtypes = [vptr, C.c_int]
         lib.ocp_b200_get_profile.argtypes = [vptr, dptr, C.POINTER(C.c_longlong), C.c_int]
         lib.ocp_b200_get_phase_cycles.argtypes = [vptr, C.POINTER(C.c_longlong)]
@@ -291,6 +292,14 @@ class Solver:
         _check(cuda_lib().ocp_b200_get_dims(self._h, *[C.byref(x) for x in v]))
         return dict(n=v[0].value, m=v[1].value, nnz_h=v[2].value, nnz_a=v[3].value, smem_bytes=v[4].value,
                     resident=v[5].value)
+
+    def launch_plan(self) -> dict:
+        """ocp_b200_get_plan: the two launch plans and the block structure of K (see OCP_B200_PLAN_*)."""
+        v = (C.c_int * 16)()
+        _check(cuda_lib().ocp_b200_get_plan(self._h, v, 16))
+        keys = ("place", "threads", "smem_bytes", "ctas_per_sm", "slab_kb")
+        return dict(wide=dict(zip(keys, v[0:5])), deep=dict(zip(keys, v[5:10])), tri_ok=v[10], tri_np=v[11], tri_bs=v[12],
+                    tri_nb=v[13], nnz_p=v[14], num_sms=v[15])
 
     def solve_batch(self, frames, p, lbx, ubx, lbg, ubg, x_inout, f_out=None, stats=None):
         """ocp_b200_solve_batch: host buffers, x_inout [B, N] updated in place."""

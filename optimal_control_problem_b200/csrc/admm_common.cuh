@@ -21,8 +21,9 @@ typedef uint16_t idx_t;
 // K-assembly program (direct kernel): one entry per structurally non-zero element of the bordered
 // block-tridiagonal K = P + sigma I + A' diag(rho) A that has to be computed, with the products
 // sum_r rho_r A_ri A_rj encoded as RUNS of consecutive positions in columns i and j of A whose rows
-// coincide one-to-one (host-side merge of the two sorted columns, done once per pattern).
-struct KRun { uint16_t ka, kc, len, pad; };
+// coincide one-to-one AND are consecutive rows row0, row0 + 1, ... (host-side merge of the two sorted
+// columns, done once per pattern), so that the constraint type of every product needs no index lookup.
+struct KRun { uint16_t ka, kc, len, row0; };
 struct KEntry {
   uint32_t dest0, dest1;   // (array << 30) | offset; array 0 = Dinv, 1 = Lsub, 2 = Lp, 3 = Dp; dest1 = mirror or 0xffffffff
   int32_t ppos;            // position of P_ij in the symmetrised P values, or -1

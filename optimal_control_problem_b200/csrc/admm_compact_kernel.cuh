@@ -1,0 +1,515 @@
+// admm_compact_kernel.cuh -- the throughput kernel of the batched ADMM QP solve for sm_100a:
+// FOUR (or three) CTAs per SM, 128 threads each.
+//
+// Same algorithm, same arithmetic order and the same factorisation / solve code (tri_fast.cuh,
+// tri_twisted.cuh) as admm_direct_kernel.cuh -- OSQP set-up + ADMM + SQP update of B independent QPs,
+// src/sqp_solver/CuCaQP.cpp:271-288, 183-224 and SQPOptimizationSolver.cpp:171-177 of the reference --
+// with a different placement of the per-instance state.  The kernel is bound by dependent-instruction
+// latency, not by bandwidth: what raises throughput is the number of instances an SM
+// works on at the same time (profiles/r2_probe_occupancy.txt: 1 -> 2 -> 3 -> 4 CTAs/SM scale 1 : 1.73 :
+// 2.29 : 2.94), and what limits that number is shared memory.  Per CTA here (H = 20 quadrotor: 50 KB,
+// against 109 KB of the two-CTA plan):
+//   * gather targets (solve vector b, x, w = rho z - y), the row-streamed z, y, the constraint types and
+//     the A values stay in shared memory;
+//   * index arrays are stage-periodic templates (periodic_index.h): 5 KB instead of 22 KB;
+//   * everything that is read once per phase by the thread that owns the element -- q, l, u, D, E, the
+//     P values, the Ruiz by-products -- lives in the CTA's global slab next to the factor (L2-resident)
+//     and is streamed, one coalesced access per element;
+//   * buffers are shared by phase: the Ruiz scratch (column / row scales, P values) and the scratch of
+//     the factorisation (block staging, chain-step products) overlay the iteration vectors, which hold
+//     nothing before the cold start; a refactorisation after a rho update parks x, z, y in the slab.
+#pragma once
+
+#include "admm_direct_kernel.cuh"
+#include "periodic_index.h"
+
+namespace ocpb200 {
+namespace compact {
+
+using direct::Rho;
+using direct::Work;
+
+// shared memory and slab layout (doubles); the same function runs on the host (plan) and on the device (carve)
+struct Layout {
+  // shared
+  size_t b, x, w, z, y, vend;       // iteration vectors; [b, vend) is also the set-up / factorisation scratch
+  size_t aval, ctype, dp, xp, piv, arena, smem_doubles;
+  // overlays of [b, vend)
+  size_t rscale, psm;               // Ruiz: row scales on x|w, P values on z|y   (column scales are b itself)
+  size_t dp2, s, sp, stage;         // factorisation scratch
+  int s_stride, sp_stride, stage_stride;
+  // slab
+  size_t dinv, lsub, lp, q, l, u, D, E, pval, dx, dy, an, cn, sx, sz, sy, slab_doubles;
+  bool ok;
+};
+
+__host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_words) {
+  auto ev = [](size_t v) { return (v + 1) & ~size_t(1); };
+  const size_t n = ev(P.n), m = ev(P.m), np = P.tri_np, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb;
+  Layout L{};
+  size_t o = 0;
+  L.b = o; o += n; L.x = o; o += n; L.w = o; o += m; L.z = o; o += m; L.y = o; o += m;
+  const size_t vlen = o;
+  L.s_stride = static_cast<int>(ev(bs * ld)); L.sp_stride = static_cast<int>(ev(np * bs)); L.stage_stride = L.s_stride;
+  size_t f = 0;
+  L.dp2 = f; f += ev(2 * np * (np + 1));
+  L.s = f; f += 2 * size_t(L.s_stride);
+  L.sp = f; f += 2 * size_t(L.sp_stride);
+  L.stage = f; f += 4 * size_t(L.stage_stride);
+  L.vend = f > vlen ? f : vlen;
+  o = L.vend;
+  L.rscale = L.x;   // m doubles on x|w
+  L.psm = L.z;      // nnz_p doubles on z|y
+  L.ok = ev(P.nnz_p) <= 2 * m && m <= n + m;
+  L.aval = o; o += ev(P.nnz_a);
+  L.ctype = o; o += ev((size_t(P.m) + 7) / 8);
+  L.dp = o; o += ev(np * (np + 1));
+  L.xp = o; o += ev(np + 2);
+  L.piv = o; o += 64;
+  L.arena = o; o += ev((size_t(arena_words) + 1) / 2);
+  L.smem_doubles = o;
+  size_t g = 0;
+  L.dinv = g; g += nb * bs * ld; L.lsub = g; g += nb * bs * ld; L.lp = g; g += ev(np * nb * bs);
+  L.q = g; g += n; L.l = g; g += m; L.u = g; g += m; L.D = g; g += n; L.E = g; g += m;
+  L.pval = g; g += ev(P.nnz_p); L.dx = g; g += n; L.dy = g; g += m; L.an = g; g += n; L.cn = g; g += n;
+  L.sx = g; g += n; L.sz = g; g += m; L.sy = g; g += m;
+  L.slab_doubles = (g + 15) & ~size_t(15);
+  return L;
+}
+
+struct Ctx {
+  const uint32_t* ar;   // arena in shared memory
+  double *rscale, *psm; // Ruiz overlays
+  double *an, *cn, *sx, *sz, *sy;   // slab: Ruiz by-products, parking space of a refactorisation
+  double* pslab;        // slab copy of the scaled P values
+};
+
+// (v may be a slab array written earlier in the launch by other threads of the CTA: no __restrict__)
+__device__ __forceinline__ double col_dot_A(const CompactIdx& C, const uint32_t* ar, const double* __restrict__ Aval,
+                                            const double* v, int j) {
+  const PSpan s = pspan_dev(C.acol, ar, j);
+  const uint32_t* te = ar + C.acol.tent_off;
+  const double* av = Aval + s.kshift;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int kt = s.kt0; kt < s.kt1; ++kt) acc += av[kt] * v[pvalue(te[kt], s.q)];
+  return acc;
+}
+__device__ __forceinline__ double col_dot_P(const CompactIdx& C, const uint32_t* ar, const double* Pval,
+                                            const double* v, int j) {
+  const PSpan s = pspan_dev(C.pcol, ar, j);
+  const uint32_t* te = ar + C.pcol.tent_off;
+  const double* pv = Pval + s.kshift;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int kt = s.kt0; kt < s.kt1; ++kt) acc += pv[kt] * v[pvalue(te[kt], s.q)];
+  return acc;
+}
+// f(row, sum_k A[row][k] * src[k]) for every row, one thread per row
+template <typename F>
+__device__ __forceinline__ void for_rows_A(const CompactIdx& C, const uint32_t* ar, int m, const double* __restrict__ Aval,
+                                           const double* src, F f) {
+  const uint32_t* tc = ar + C.arow.tent_off;
+  const uint32_t* tp = ar + C.arow.tent2_off;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const PSpan s = pspan_dev(C.arow, ar, i);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int kt = s.kt0; kt < s.kt1; ++kt) acc += Aval[pvalue(tp[kt], s.q)] * src[pvalue(tc[kt], s.q)];
+    f(i, acc);
+  }
+}
+
+template <int BS>
+__device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, const ocp_b200_settings& S, const SolveArgs& A,
+                                      Work& W, const Ctx& X, Reducer& R, int inst, QpResult& out) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int n = P.n, m = P.m;
+  const double sigma = S.sigma, relax = S.relax;
+  const uint32_t* const ar = X.ar;
+  PhaseClock clk(A.phase);
+  W.phase = A.phase;
+
+  // ---- load (osqp_setup copies its inputs): values, q, bounds clamped to +-1e30 ------------
+  {
+    const double* hv = A.h_vals + size_t(inst) * A.ld_h;
+    const double* av = A.a_vals + size_t(inst) * A.ld_a;
+    const double* qv = A.q + size_t(inst) * A.ld_n;
+    const double* lv = A.l + size_t(inst) * A.ld_m;
+    const double* uv = A.u + size_t(inst) * A.ld_m;
+    for (int k = tid; k < P.nnz_a; k += T) W.Aval[k] = av[k];
+    for (int k = tid; k < P.nnz_p; k += T) { const int s = P.p_src[k]; X.psm[k] = s >= 0 ? hv[s] : 0.0; }
+    for (int j = tid; j < n; j += T) { W.q[j] = qv[j]; W.D[j] = 1.0; }
+    double bad[1] = {0.0};
+    for (int i = tid; i < m; i += T) {
+      const double lo = lv[i], hi = uv[i];
+      if (lo > hi) bad[0] = 1.0;
+      W.l[i] = fmax(lo, -kInfty);
+      W.u[i] = fmin(hi, kInfty);
+      W.E[i] = 1.0;
+    }
+    block_reduce<1, true>(bad, R);
+    if (bad[0] > 0.0) {  // osqp_setup rejects l > u; the reference then adds no usable step
+      for (int j = tid; j < n; j += T) W.x[j] = 0.0;
+      for (int i = tid; i < m; i += T) W.y[i] = 0.0;
+      __syncthreads();
+      out = QpResult{OCP_B200_QP_UNSOLVED, 0, 0, 0, 0, 0.0, 0.0, S.rho};
+      return;
+    }
+  }
+  clk.lap(OCP_B200_PHASE_LOAD);
+
+  // ---- Ruiz equilibration (scale_data).  Shared: column scales (b), row scales (x|w), P values (z|y),
+  // A values.  Slab, element j / i always touched by the same thread: q, D, E, the inf-norms of the
+  // scaled A / P columns (by-products of pass k that give the column norms of pass k + 1).
+  double c = 1.0;
+  {
+    const uint32_t* ta = ar + C.acol.tent_off;
+    const uint32_t* tr2 = ar + C.arow.tent2_off;
+    const uint32_t* tp = ar + C.pcol.tent_off;
+    double* const cs = W.b;
+    double* const rs = X.rscale;
+    double* const Ps = X.psm;
+    for (int pass = 0; pass < S.scaling_iters; ++pass) {
+      for (int j = tid; j < n; j += T) {
+        double dn = 0.0;
+        if (pass == 0) {
+          const PSpan sp = pspan_dev(C.pcol, ar, j);
+#pragma unroll 4
+          for (int kt = sp.kt0; kt < sp.kt1; ++kt) dn = fmax(dn, fabs(Ps[kt + sp.kshift]));
+          const PSpan sa = pspan_dev(C.acol, ar, j);
+#pragma unroll 4
+          for (int kt = sa.kt0; kt < sa.kt1; ++kt) dn = fmax(dn, fabs(W.Aval[kt + sa.kshift]));
+        } else {
+          dn = fmax(X.cn[j], X.an[j]);
+        }
+        cs[j] = 1.0 / sqrt(limit_scaling(dn));
+      }
+      for (int i = tid; i < m; i += T) {
+        const PSpan s = pspan_dev(C.arow, ar, i);
+        double en = 0.0;
+#pragma unroll 4
+        for (int kt = s.kt0; kt < s.kt1; ++kt) en = fmax(en, fabs(W.Aval[pvalue(tr2[kt], s.q)]));
+        rs[i] = 1.0 / sqrt(limit_scaling(en));
+      }
+      __syncthreads();
+      double red[2] = {0.0, 0.0};  // sum of P column norms, max |q|
+      for (int j = tid; j < n; j += T) {
+        const double dj = cs[j];
+        const double q0 = W.q[j], d0 = W.D[j];   // slab loads issued before the column loops
+        double cn = 0.0, an = 0.0;
+        const PSpan sp = pspan_dev(C.pcol, ar, j);
+        for (int kt = sp.kt0; kt < sp.kt1; ++kt) {
+          const double v = Ps[kt + sp.kshift] * cs[pvalue(tp[kt], sp.q)] * dj;
+          Ps[kt + sp.kshift] = v;
+          cn = fmax(cn, fabs(v));
+        }
+        const PSpan sa = pspan_dev(C.acol, ar, j);
+#pragma unroll 4
+        for (int kt = sa.kt0; kt < sa.kt1; ++kt) {
+          const double v = W.Aval[kt + sa.kshift] * (rs[pvalue(ta[kt], sa.q)] * dj);
+          W.Aval[kt + sa.kshift] = v;
+          an = fmax(an, fabs(v));
+        }
+        X.an[j] = an;      // inf-norm of the scaled A column
+        X.cn[j] = cn;      // inf-norm of the scaled P column, before the cost factor
+        const double qj = q0 * dj;
+        W.q[j] = qj;
+        W.D[j] = d0 * dj;
+        red[0] += cn;
+        red[1] = fmax(red[1], fabs(qj));
+      }
+      for (int i = tid; i < m; i += T) W.E[i] *= rs[i];
+      double sum[1] = {red[0]}, mx[1] = {red[1]};
+      block_reduce<1, false>(sum, R);
+      block_reduce<1, true>(mx, R);
+      const double ct = 1.0 / limit_scaling(fmax(sum[0] / double(n), limit_scaling(mx[0])));
+      for (int k = tid; k < P.nnz_p; k += T) Ps[k] *= ct;
+      for (int j = tid; j < n; j += T) { W.q[j] *= ct; X.cn[j] *= ct; }
+      c *= ct;
+      __syncthreads();
+    }
+  }
+  const double cinv = 1.0 / c;
+
+  // ---- scaled bounds, constraint types (set_rho_vec); the scaled P values move to the slab ----
+  double rho = fmin(fmax(S.rho, kRhoMin), kRhoMax);
+  for (int i = tid; i < m; i += T) {
+    const double e = W.E[i];
+    const double lo = W.l[i] * e, hi = W.u[i] * e;
+    W.l[i] = lo; W.u[i] = hi;
+    signed char ct = 0;
+    if (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ct = -1;
+    else if (hi - lo < kRhoTol) ct = 1;
+    W.ctype[i] = ct;
+  }
+  for (int k = tid; k < P.nnz_p; k += T) X.pslab[k] = X.psm[k];
+  __syncthreads();
+  W.Pval = X.pslab;
+  Rho rv(rho);
+  clk.lap(OCP_B200_PHASE_SCALE);
+  direct::tri_assemble_program(P, W, rv, sigma);
+  clk.lap(OCP_B200_PHASE_KKT_ASSEMBLE);
+  direct::tri_factor_twisted<BS>(P, W);   // scratch: the iteration vectors (nothing lives there yet)
+  clk.lap(OCP_B200_PHASE_FACTOR);
+  // ---- cold start ----
+  for (int j = tid; j < n; j += T) W.x[j] = 0.0;
+  for (int i = tid; i < m; i += T) { W.z[i] = 0.0; W.y[i] = 0.0; W.w[i] = 0.0; }
+  __syncthreads();
+
+  const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : 4 * S.check_termination;
+  int status = OCP_B200_QP_UNSOLVED, iter = 0, solves = 0, rho_updates = 0, checks = 0, n_trace = 0;
+  double prim_res = 0.0, dual_res = 0.0;
+  bool done = false;
+
+  for (iter = 1; iter <= S.admm_max_iter && !done; ++iter) {
+    // ---- right-hand side of the reduced KKT system: sigma x - q + A'(rho z - y) --------------
+    for (int j = tid; j < n; j += T) {
+      const double qj = W.q[j];   // slab
+      W.b[j] = (sigma * W.x[j] - qj) + col_dot_A(C, ar, W.Aval, W.w, j);
+    }
+    __syncthreads();
+    clk.lap(OCP_B200_PHASE_RHS);
+    direct::tri_solve_twisted<BS>(P, W);   // b <- x~
+    ++solves;
+    clk.lap(OCP_B200_PHASE_SOLVE);
+
+    // ---- x, z, y updates with relaxation and projection (update_x / update_z / update_y) ----
+    const bool can_check = S.check_termination > 0 && (iter % S.check_termination == 0);
+    const bool last_iter = iter == S.admm_max_iter;
+    const bool rho_time = S.adaptive_rho && rho_interval > 0 && (iter % rho_interval == 0);
+    const bool want_info = can_check || rho_time || last_iter;
+    {
+      const uint32_t* tc = ar + C.arow.tent_off;
+      const uint32_t* tp = ar + C.arow.tent2_off;
+      for (int i = tid; i < m; i += T) {
+        const double lo = W.l[i], hi = W.u[i];   // slab: requested before the row product
+        const PSpan s = pspan_dev(C.arow, ar, i);
+        double zt = 0.0;
+#pragma unroll 4
+        for (int kt = s.kt0; kt < s.kt1; ++kt) zt += W.Aval[pvalue(tp[kt], s.q)] * W.b[pvalue(tc[kt], s.q)];
+        const signed char ct = W.ctype[i];
+        const double rh = rv.of(ct);
+        const double zr = relax * zt + (1.0 - relax) * W.z[i];
+        const double zn = fmin(fmax(zr + rv.inv(ct) * W.y[i], lo), hi);
+        const double dy = rh * (zr - zn);
+        const double yn = W.y[i] + dy;
+        W.y[i] = yn;
+        W.z[i] = zn;
+        W.w[i] = rh * zn - yn;
+        if (want_info) W.dy[i] = dy;
+      }
+    }
+    for (int j = tid; j < n; j += T) {
+      const double xo = W.x[j];
+      const double xn = relax * W.b[j] + (1.0 - relax) * xo;
+      if (want_info) W.dx[j] = xn - xo;
+      W.x[j] = xn;
+    }
+    __syncthreads();
+    clk.lap(OCP_B200_PHASE_UPDATE);
+    if (!want_info) continue;
+
+    // ---- update_info: residuals of the unscaled problem ------------------------------------
+    ++checks;
+    double mx[kRedWidth];
+#pragma unroll
+    for (int k = 0; k < kRedWidth; ++k) mx[k] = 0.0;
+    for_rows_A(C, ar, m, W.Aval, W.x, [&](int i, double ax) {
+      const double einv = 1.0 / W.E[i];
+      const double zi = W.z[i];
+      const double rp = ax - zi;
+      mx[0] = fmax(mx[0], fabs(einv * rp));
+      mx[1] = fmax(mx[1], fabs(einv * ax));
+      mx[2] = fmax(mx[2], fabs(einv * zi));
+      mx[3] = fmax(mx[3], fabs(rp));
+      mx[4] = fmax(mx[4], fabs(ax));
+      mx[5] = fmax(mx[5], fabs(zi));
+    });
+    for (int j = tid; j < n; j += T) {
+      const double dinv = 1.0 / W.D[j];
+      const double qj = W.q[j];
+      const double px = col_dot_P(C, ar, W.Pval, W.x, j);
+      const double aty = col_dot_A(C, ar, W.Aval, W.y, j);
+      const double rd = qj + px + aty;
+      mx[6] = fmax(mx[6], fabs(dinv * rd));
+      mx[7] = fmax(mx[7], fabs(dinv * qj));
+      mx[8] = fmax(mx[8], fabs(dinv * px));
+      mx[9] = fmax(mx[9], fabs(dinv * aty));
+      mx[10] = fmax(mx[10], fabs(rd));
+      mx[11] = fmax(mx[11], fabs(qj));
+      mx[12] = fmax(mx[12], fabs(px));
+      mx[13] = fmax(mx[13], fabs(aty));
+    }
+    block_reduce<kRedWidth, true>(mx, R);
+    prim_res = mx[0];
+    dual_res = cinv * mx[6];
+
+    if (can_check || last_iter) {
+      // ---- check_termination ---------------------------------------------------------------
+      const double eps_prim = S.eps_abs + S.eps_rel * fmax(mx[2], mx[1]);
+      const double eps_dual = S.eps_abs + S.eps_rel * cinv * fmax(mx[7], fmax(mx[9], mx[8]));
+      const bool prim_ok = prim_res < eps_prim, dual_ok = dual_res < eps_dual;
+      bool prim_inf = false, dual_inf = false;
+      if (!prim_ok) {
+        // is_primal_infeasible: dy projected on the polar of the recession cone of [l, u]
+        double a2[1] = {0.0};
+        for (int i = tid; i < m; i += T) {
+          double dy = W.dy[i];
+          const double lo = W.l[i], hi = W.u[i];
+          if (hi > kInfty * kMinScaling) {
+            if (lo < -kInfty * kMinScaling) dy = 0.0; else dy = fmin(dy, 0.0);
+          } else if (lo < -kInfty * kMinScaling) {
+            dy = fmax(dy, 0.0);
+          }
+          W.dy[i] = dy;
+          a2[0] = fmax(a2[0], fabs(W.E[i] * dy));
+        }
+        block_reduce<1, true>(a2, R);
+        const double norm_dy = a2[0];
+        if (norm_dy > kDivisionTol) {
+          double lhs[1] = {0.0};
+          for (int i = tid; i < m; i += T) lhs[0] += W.u[i] * fmax(W.dy[i], 0.0) + W.l[i] * fmin(W.dy[i], 0.0);
+          block_reduce<1, false>(lhs, R);
+          if (lhs[0] < -S.eps_prim_inf * norm_dy) {
+            // A' dy gathers dy: the slab copy was written by other threads of this CTA
+            __syncthreads();
+            double na[1] = {0.0};
+            for (int j = tid; j < n; j += T) na[0] = fmax(na[0], fabs(col_dot_A(C, ar, W.Aval, W.dy, j) / W.D[j]));
+            block_reduce<1, true>(na, R);
+            prim_inf = na[0] < S.eps_prim_inf * norm_dy;
+          }
+        }
+      }
+      if (!dual_ok) {
+        // is_dual_infeasible
+        double a2[1] = {0.0};
+        for (int j = tid; j < n; j += T) a2[0] = fmax(a2[0], fabs(W.D[j] * W.dx[j]));
+        block_reduce<1, true>(a2, R);
+        const double norm_dx = a2[0];
+        if (norm_dx > kDivisionTol) {
+          double qdx[1] = {0.0};
+          for (int j = tid; j < n; j += T) qdx[0] += W.q[j] * W.dx[j];
+          block_reduce<1, false>(qdx, R);
+          if (qdx[0] < -c * S.eps_dual_inf * norm_dx) {
+            double np_[1] = {0.0};
+            for (int j = tid; j < n; j += T) np_[0] = fmax(np_[0], fabs(col_dot_P(C, ar, W.Pval, W.dx, j) / W.D[j]));
+            block_reduce<1, true>(np_, R);
+            if (np_[0] < c * S.eps_dual_inf * norm_dx) {
+              double viol[1] = {0.0};
+              for_rows_A(C, ar, m, W.Aval, W.dx, [&](int i, double adx) {
+                const double a = adx / W.E[i];
+                if ((W.u[i] < kInfty * kMinScaling && a > S.eps_dual_inf * norm_dx) ||
+                    (W.l[i] > -kInfty * kMinScaling && a < -S.eps_dual_inf * norm_dx)) viol[0] = 1.0;
+              });
+              block_reduce<1, true>(viol, R);
+              dual_inf = viol[0] == 0.0;
+            }
+          }
+        }
+      }
+      int st = -1;
+      if (prim_ok && dual_ok) st = OCP_B200_QP_SOLVED;
+      else if (prim_inf) st = OCP_B200_QP_PRIMAL_INFEASIBLE;
+      else if (dual_inf) st = OCP_B200_QP_DUAL_INFEASIBLE;
+      if (A.trace && inst == 0 && can_check && n_trace < A.max_trace) {
+        if (tid == 0) {
+          double* tr = A.trace + size_t(n_trace) * OCP_B200_TRACE_WIDTH;
+          tr[0] = iter; tr[1] = prim_res; tr[2] = dual_res; tr[3] = rho; tr[4] = solves;
+          tr[5] = st < 0 ? OCP_B200_QP_UNSOLVED : st;
+        }
+        ++n_trace;
+      }
+      if (st >= 0) { status = st; done = true; clk.lap(OCP_B200_PHASE_CHECK); continue; }
+      if (last_iter) {
+        // approximate termination test with 10x tolerances, then MAX_ITER_REACHED
+        const double ep = 10.0 * S.eps_abs + 10.0 * S.eps_rel * fmax(mx[2], mx[1]);
+        const double ed = 10.0 * S.eps_abs + 10.0 * S.eps_rel * cinv * fmax(mx[7], fmax(mx[9], mx[8]));
+        status = (prim_res < ep && dual_res < ed) ? OCP_B200_QP_SOLVED_INACCURATE : OCP_B200_QP_MAX_ITER_REACHED;
+        done = true;
+        continue;
+      }
+    }
+
+    if (rho_time) {
+      // ---- adapt_rho: estimate from SCALED residuals, applied when it moved by > tolerance
+      const double pr = mx[3] / (fmax(mx[5], mx[4]) + 1e-10);
+      const double dr = mx[10] / (fmax(mx[11], fmax(mx[13], mx[12])) + 1e-10);
+      double est = rho * sqrt(pr / (dr + 1e-10));
+      est = fmin(fmax(est, kRhoMin), kRhoMax);
+      if (est > rho * S.adaptive_rho_tolerance || est < rho / S.adaptive_rho_tolerance) {
+        rho = est;
+        ++rho_updates;
+        rv = Rho(rho);
+        // the factorisation works in the space of the iteration vectors: park x, z, y in the slab
+        // (element i written and read back by the same thread)
+        __syncthreads();
+        for (int j = tid; j < n; j += T) X.sx[j] = W.x[j];
+        for (int i = tid; i < m; i += T) { X.sz[i] = W.z[i]; X.sy[i] = W.y[i]; }
+        __syncthreads();
+        direct::tri_assemble_program(P, W, rv, sigma);
+        direct::tri_factor_twisted<BS>(P, W);
+        for (int j = tid; j < n; j += T) W.x[j] = X.sx[j];
+        for (int i = tid; i < m; i += T) {
+          const double zi = X.sz[i], yi = X.sy[i];
+          W.z[i] = zi; W.y[i] = yi;
+          W.w[i] = rv.of(W.ctype[i]) * zi - yi;
+        }
+        __syncthreads();
+      }
+    }
+    clk.lap(OCP_B200_PHASE_CHECK);
+  }
+  if (!done) { status = OCP_B200_QP_MAX_ITER_REACHED; }
+  if (A.trace && inst == 0 && tid == 0 && A.n_trace) *A.n_trace = n_trace;
+  const int iters_done = done ? iter - 1 : S.admm_max_iter;
+  out = QpResult{status, iters_done, solves, rho_updates, checks, prim_res, dual_res, rho};
+
+  // ---- store_solution: unscale in place (x <- D x, y <- E y / c), or NaN for a certificate
+  const bool has_sol = status != OCP_B200_QP_PRIMAL_INFEASIBLE && status != OCP_B200_QP_DUAL_INFEASIBLE;
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  for (int j = tid; j < n; j += T) W.x[j] = has_sol ? W.D[j] * W.x[j] : nanv;
+  for (int i = tid; i < m; i += T) W.y[i] = has_sol ? cinv * W.E[i] * W.y[i] : nanv;
+  __syncthreads();
+}
+
+// persistent kernel: CTAs pull instances from A.counter
+template <int BS, int kThreads, int kBlocksPerSm>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSm)
+admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_settings S, const SolveArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red_buf[2 * (kThreads / 32) * kRedWidth];
+  __shared__ int s_inst;
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* gl = A.slab + size_t(blockIdx.x) * A.slab_doubles;
+  const Layout L = make_layout(P, C.arena_words);
+  Work W{};
+  W.b = sm + L.b; W.x = sm + L.x; W.w = sm + L.w; W.z = sm + L.z; W.y = sm + L.y;
+  W.Aval = sm + L.aval; W.ctype = reinterpret_cast<signed char*>(sm + L.ctype);
+  W.Dp = sm + L.dp; W.xp = sm + L.xp; W.piv = sm + L.piv;
+  W.Dp2 = sm + L.dp2; W.S = sm + L.s; W.Sp = sm + L.sp; W.stage = sm + L.stage;
+  W.s_stride = L.s_stride; W.sp_stride = L.sp_stride; W.stage_stride = L.stage_stride;
+  W.ring_bar = nullptr; W.ring_phase = nullptr; W.ring_slots = 0;
+  W.Dinv = gl + L.dinv; W.Lsub = gl + L.lsub; W.Lp = gl + L.lp;
+  W.q = gl + L.q; W.l = gl + L.l; W.u = gl + L.u; W.D = gl + L.D; W.E = gl + L.E;
+  W.Pval = gl + L.pval; W.dx = gl + L.dx; W.dy = gl + L.dy;
+  W.idx = nullptr; W.phase = nullptr;
+  uint32_t* ar = reinterpret_cast<uint32_t*>(sm + L.arena);
+  for (int k = threadIdx.x; k < C.arena_words; k += kThreads) ar[k] = C.arena[k];
+  Ctx X{ar, sm + L.rscale, sm + L.psm, gl + L.an, gl + L.cn, gl + L.sx, gl + L.sz, gl + L.sy, gl + L.pval};
+  __syncthreads();
+  Reducer R{red_buf, 0, (kThreads / 32) * kRedWidth};
+  while (true) {
+    if (threadIdx.x == 0) s_inst = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int inst = s_inst;
+    __syncthreads();
+    if (inst >= A.B) break;
+    QpResult res;
+    solve_instance<BS>(P, C, S, A, W, X, R, inst, res);
+    write_outputs(P, A, W.x, W.y, R, inst, res);
+  }
+}
+
+}  // namespace compact
+}  // namespace ocpb200

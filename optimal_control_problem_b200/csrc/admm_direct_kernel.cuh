@@ -198,7 +198,7 @@ __device__ inline void tri_assemble_program(const PatternDev& P, const Work& W, 
 #pragma unroll 4
       for (int t = 0; t < run.len; ++t) {
         const int ka = run.ka + t, kc = run.kc + t;
-        s += rho.of(W.ctype[P.a_rowidx[ka]]) * W.Aval[ka] * W.Aval[kc];
+        s += rho.of(W.ctype[run.row0 + t]) * W.Aval[ka] * W.Aval[kc];
       }
     }
     arr[ent.dest0 >> 30][ent.dest0 & 0x3fffffffu] = s;

@@ -1,0 +1,18 @@
+// compact_launch.h -- host-side entry points of the compact throughput kernel (direct_compact.cu).
+#pragma once
+#include "admm_common.cuh"
+#include "direct_launch.h"
+#include "periodic_index.h"
+
+namespace ocpb200 {
+namespace compact {
+
+cudaError_t kernel_info(int bs, direct::KernelInfo* out);
+cudaError_t set_max_dynamic_smem(int bs, int bytes);
+cudaError_t occupancy(int bs, int dyn_smem, int* per_sm);
+cudaError_t launch(int bs, int grid, int dyn_smem, cudaStream_t st, const PatternDev& P, const CompactIdx& C,
+                   const ocp_b200_settings& S, const SolveArgs& A);
+void plan_sizes(const PatternDev& P, int arena_words, size_t* smem_doubles, size_t* slab_doubles, bool* ok);
+
+}  // namespace compact
+}  // namespace ocpb200

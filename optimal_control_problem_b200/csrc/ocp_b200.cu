@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "admm_pcg_kernel.cuh"
+#include "compact_launch.h"
 #include "direct_launch.h"
 #include "ocp_b200_model.h"
 
@@ -107,6 +108,10 @@ struct ocp_b200_solver {
   DevBuf<int> d_int;
   DevBuf<ocpb200::KEntry> d_kent;
   DevBuf<ocpb200::KRun> d_krun;
+  // stage-periodic templates of the index structures (compact throughput kernel); compact_ok: they exist
+  DevBuf<uint32_t> d_arena;
+  ocpb200::CompactIdx cidx{};
+  int compact_ok = 0;
   // stage library
   void* lib = nullptr;
   model_assemble_fn assemble = nullptr;
@@ -282,10 +287,11 @@ int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
         const int ea = ac[i + 1], ec = ac[j + 1];
         while (ka < ea && kc < ec) {
           if (ar[ka] == ar[kc]) {
-            if (e.nruns > 0 && runs.back().ka + runs.back().len == ka && runs.back().kc + runs.back().len == kc) {
+            if (e.nruns > 0 && runs.back().ka + runs.back().len == ka && runs.back().kc + runs.back().len == kc &&
+                runs.back().row0 + runs.back().len == ar[ka]) {
               runs.back().len++;
             } else {
-              runs.push_back({static_cast<uint16_t>(ka), static_cast<uint16_t>(kc), 1, 0});
+              runs.push_back({static_cast<uint16_t>(ka), static_cast<uint16_t>(kc), 1, static_cast<uint16_t>(ar[ka])});
               e.nruns++;
             }
             ++ka; ++kc;
@@ -325,6 +331,42 @@ int upload_pattern(ocp_b200_solver* s, int num_blocks, const int* block_ptr) {
         P.kprog_entries = static_cast<int>(ents.size());
         P.kprog = s->d_kent.p; P.kruns = s->d_krun.p;
       }
+    }
+  }
+  // stage-periodic templates of the CSC / CSR structures of A and of the symmetrised P (periodic_index.h)
+  s->compact_ok = 0;
+  if (P.tri_ok && P.kprog_entries > 0 && rows_long.empty()) {
+    std::vector<int> periods;
+    for (int p = 1; p <= 96; ++p) periods.push_back(p);
+    ocpb200::PIndexHost hc, hr, hp;
+    const bool built = ocpb200::build_periodic_index(ac, ar, {}, periods, hc) &&
+                       ocpb200::build_periodic_index(rowptr, colidx, perm, periods, hr) &&
+                       ocpb200::build_periodic_index(pc, pr, {}, periods, hp);
+    const size_t maxreg = std::max({hc.reg.size(), hr.reg.size(), hp.reg.size()});
+    if (built && maxreg <= size_t(ocpb200::kMaxDevRegions)) {
+      std::vector<uint32_t> arena32;
+      auto place = [&](const ocpb200::PIndexHost& h, ocpb200::PIndexDev& d) {
+        d.nreg = static_cast<int>(h.reg.size());
+        for (int r = 0; r < ocpb200::kMaxDevRegions; ++r) {
+          d.ibound[r] = r < d.nreg ? h.reg[r].i1 : 0x7fffffff;
+          d.kbound[r] = r < d.nreg ? h.reg[r].k1 : 0x7fffffff;
+        }
+        d.reg_off = static_cast<int>(arena32.size());
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(h.reg.data());
+        arena32.insert(arena32.end(), rw, rw + h.reg.size() * (sizeof(ocpb200::PRegion) / 4));
+        d.tptr_off = static_cast<int>(arena32.size());
+        arena32.insert(arena32.end(), h.tptr.begin(), h.tptr.end());
+        d.tent_off = static_cast<int>(arena32.size());
+        arena32.insert(arena32.end(), h.tent.begin(), h.tent.end());
+        d.tent2_off = h.tent2.empty() ? -1 : static_cast<int>(arena32.size());
+        arena32.insert(arena32.end(), h.tent2.begin(), h.tent2.end());
+      };
+      place(hc, s->cidx.acol); place(hr, s->cidx.arow); place(hp, s->cidx.pcol);
+      CUDA_TRY(s->d_arena.reserve(arena32.size()));
+      CUDA_TRY(cudaMemcpy(s->d_arena.p, arena32.data(), arena32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      s->cidx.arena = s->d_arena.p;
+      s->cidx.arena_words = static_cast<int>(arena32.size());
+      s->compact_ok = 1;
     }
   }
   return OCP_B200_OK;
@@ -401,6 +443,8 @@ int plan_launch(ocp_b200_solver* s) {
       }
       int occ = 1;
       CUDA_TRY(D::occupancy(place, L.smem_bytes, &occ));
+      // OCP_B200_MAX_CTAS_PER_SM caps the residency the occupancy calculator allows (diagnostics)
+      if (const char* cap = std::getenv("OCP_B200_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, std::atoi(cap)));
       L.max_ctas = std::max(1, occ) * s->num_sms;
       return OCP_B200_OK;
     };
@@ -429,6 +473,28 @@ int plan_launch(ocp_b200_solver* s) {
     else if (env && !std::strcmp(env, "big") && fits_big) deep = wide = 3;
     RC_TRY(make_plan(deep, s->deep));
     RC_TRY(make_plan(wide, s->wide));
+    // compact throughput plan (admm_compact_kernel.cuh): 128 threads, index templates, streamed slab
+    // vectors -- taken when it puts more CTAs on an SM than the plan above (OCP_B200_PLAN=compact forces it,
+    // any other value of OCP_B200_PLAN keeps it out)
+    if (s->compact_ok && (P.tri_bs == 16 || P.tri_bs == 20) && P.tri_ld == P.tri_bs + 2 && (!env || !std::strcmp(env, "compact"))) {
+      namespace K = ocpb200::compact;
+      size_t sm_d = 0, sl_d = 0;
+      bool lay_ok = false;
+      K::plan_sizes(P, s->cidx.arena_words, &sm_d, &sl_d, &lay_ok);
+      D::KernelInfo kc{};
+      CUDA_TRY(K::kernel_info(P.tri_bs, &kc));
+      if (lay_ok && sm_d * sizeof(double) + kc.static_smem <= size_t(max_optin)) {
+        CUDA_TRY(K::set_max_dynamic_smem(P.tri_bs, max_optin - kc.static_smem));
+        int occ = 1;
+        CUDA_TRY(K::occupancy(P.tri_bs, static_cast<int>(sm_d * sizeof(double)), &occ));
+        if (const char* cap = std::getenv("OCP_B200_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, std::atoi(cap)));
+        if (occ * kc.threads > (s->wide.max_ctas / s->num_sms) * s->wide.threads || (env && occ >= 1)) {
+          s->wide.place = 4; s->wide.threads = kc.threads; s->wide.smem_bytes = static_cast<int>(sm_d * sizeof(double));
+          s->wide.smem_mask = 0; s->wide.slab_doubles = sl_d; s->wide.max_ctas = occ * s->num_sms;
+          if (env) s->deep = s->wide;
+        }
+      }
+    }
     s->place = s->wide.place; s->threads = s->wide.threads; s->smem_bytes = s->wide.smem_bytes;
     s->smem_mask = s->wide.smem_mask; s->slab_doubles = s->wide.slab_doubles;
     s->resident = s->deep.place == 1 ? 1 : 0;
@@ -521,7 +587,10 @@ int launch_admm(ocp_b200_solver* s, SolveArgs& A, cudaStream_t st) {
       CUDA_TRY(s->slab.reserve(size_t(grid) * L.slab_doubles));
       A.slab = s->slab.p;
     }
-    CUDA_TRY(ocpb200::direct::launch(L.place, grid, L.smem_bytes, st, s->pat, s->settings, A, L.smem_mask));
+    if (L.place == 4)
+      CUDA_TRY(ocpb200::compact::launch(s->pat.tri_bs, grid, L.smem_bytes, st, s->pat, s->cidx, s->settings, A));
+    else
+      CUDA_TRY(ocpb200::direct::launch(L.place, grid, L.smem_bytes, st, s->pat, s->settings, A, L.smem_mask));
   } else if (s->resident) {
     A.slab = nullptr; A.slab_doubles = 0;
     ocp_b200_settings t = s->settings;
@@ -667,7 +736,7 @@ int ocp_b200_destroy(ocp_b200_solver* s) {
   if (!s) return OCP_B200_OK;
   cudaSetDevice(s->device);
   if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
-  s->d_idx.release(); s->d_int.release(); s->d_kent.release(); s->d_krun.release();
+  s->d_idx.release(); s->d_int.release(); s->d_kent.release(); s->d_krun.release(); s->d_arena.release();
   DevBuf<double>* bufs[] = {&s->hv, &s->q, &s->av, &s->l, &s->u, &s->solx, &s->soly, &s->info, &s->slab, &s->trace,
                             &s->x, &s->p, &s->frames, &s->lbx, &s->ubx, &s->lbg, &s->ubg, &s->f, &s->stats};
   for (DevBuf<double>* b : bufs) b->release();
@@ -907,6 +976,46 @@ int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int*
   if (nnz_a) *nnz_a = s->nnz_a;
   if (smem_bytes) *smem_bytes = s->smem_bytes;
   if (resident) *resident = s->resident | (s->use_direct << 1) | (s->place << 2);
+  return OCP_B200_OK;
+}
+
+/* Test hook (not part of include/ocp_b200.h): compresses the CSC structure (ptr[nout + 1], val[nnz], optional
+ * val2[nnz]) with periodic_index.h, expands it again and returns the number of 32-bit words of the compressed
+ * form, or -1 when the structure cannot be represented / the expansion differs.  Pure host code. */
+int ocp_b200_internal_compress_index(int nout, const int* ptr, const int* val, const int* val2, int* regions) {
+  if (nout < 0 || !ptr || (!val && ptr[nout] > 0)) return -1;
+  std::vector<int> p(ptr, ptr + nout + 1), v(val, val + ptr[nout]), v2;
+  if (val2) v2.assign(val2, val2 + ptr[nout]);
+  std::vector<int> periods;
+  for (int q = 1; q <= 96; ++q) periods.push_back(q);
+  ocpb200::PIndexHost h;
+  if (!ocpb200::build_periodic_index(p, v, v2, periods, h)) return -1;
+  if (regions) *regions = static_cast<int>(h.reg.size());
+  return static_cast<int>(h.words());
+}
+
+int ocp_b200_get_plan(const ocp_b200_solver* s, int* v, int count) {
+  if (!s || !v || count < 0) return fail(OCP_B200_ERR_INVALID, "solver/v is NULL");
+  int o[OCP_B200_PLAN_COUNT] = {0};
+  const int sms = std::max(1, s->num_sms);
+  if (s->use_direct) {
+    const LaunchPlan* L[2] = {&s->wide, &s->deep};
+    for (int k = 0; k < 2; ++k) {
+      o[5 * k + 0] = L[k]->place; o[5 * k + 1] = L[k]->threads; o[5 * k + 2] = L[k]->smem_bytes;
+      o[5 * k + 3] = L[k]->max_ctas / sms; o[5 * k + 4] = static_cast<int>(L[k]->slab_doubles * sizeof(double) / 1024);
+    }
+  } else {
+    o[OCP_B200_PLAN_WIDE_PLACE] = o[OCP_B200_PLAN_DEEP_PLACE] = -1;
+    o[OCP_B200_PLAN_WIDE_THREADS] = o[OCP_B200_PLAN_DEEP_THREADS] = s->threads;
+    o[OCP_B200_PLAN_WIDE_SMEM] = o[OCP_B200_PLAN_DEEP_SMEM] = s->smem_bytes;
+    o[OCP_B200_PLAN_WIDE_CTAS_SM] = o[OCP_B200_PLAN_DEEP_CTAS_SM] = s->max_ctas / sms;
+    o[OCP_B200_PLAN_WIDE_SLAB_KB] = o[OCP_B200_PLAN_DEEP_SLAB_KB] = static_cast<int>(s->slab_doubles * sizeof(double) / 1024);
+  }
+  o[OCP_B200_PLAN_TRI_OK] = s->use_direct;
+  o[OCP_B200_PLAN_TRI_NP] = s->pat.tri_np; o[OCP_B200_PLAN_TRI_BS] = s->pat.tri_bs; o[OCP_B200_PLAN_TRI_NB] = s->pat.tri_nb;
+  o[OCP_B200_PLAN_NNZ_P] = s->nnz_p;
+  o[OCP_B200_PLAN_NUM_SMS] = s->num_sms;
+  for (int k = 0; k < count && k < OCP_B200_PLAN_COUNT; ++k) v[k] = o[k];
   return OCP_B200_OK;
 }
 

@@ -294,3 +294,34 @@ def test_sample_inputs_are_deterministic(native):
     assert (np.abs(a[:, :3]) <= 1.0).all() and (np.abs(a[:, 3:6]) <= 0.3).all() and np.allclose(a[:, 12:], 9.81 / 4)
     oa, _ = _oracle.OracleProblem("quadrotor").sample_inputs(16, 0xB202)
     assert np.array_equal(a, oa)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage-periodic index templates of the compact throughput kernel (csrc/periodic_index.h)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,horizon", [("quadrotor", 20), ("cartpole", 40), ("centroidal", 16)])
+def test_periodic_index_compression_round_trips(native, name, horizon):
+    """The builder expands what it compressed and compares (values through the outer index AND through the
+    position); here on the real CSC / CSR structures of the benchmark problems, which must shrink a lot."""
+    lib = native.cuda_lib()
+    lib.ocp_b200_internal_compress_index.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4
+    prob = native.Problem(name, horizon=horizon)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    regions = C.c_int(0)
+    ac, ar = prob.a_colptr.astype(np.int32), prob.a_rowidx.astype(np.int32)
+    words = lib.ocp_b200_internal_compress_index(prob.n, ip(ac), ip(ar), None, C.byref(regions))
+    assert 0 < words < (prob.nnz_a + prob.n) // 2 and regions.value <= 12
+    # CSR view with the CSR -> CSC position permutation as second payload
+    order = np.lexsort((np.repeat(np.arange(prob.n), np.diff(ac)), ar))
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(ar, minlength=prob.m))]).astype(np.int32)
+    colidx = np.repeat(np.arange(prob.n), np.diff(ac))[order].astype(np.int32)
+    perm = order.astype(np.int32)
+    words = lib.ocp_b200_internal_compress_index(prob.m, ip(rowptr), ip(colidx), ip(perm), C.byref(regions))
+    assert 0 < words < (2 * prob.nnz_a + prob.m) // 2 and regions.value <= 12
+    # a pattern without stage structure stays explicit (one region, no saving) but still round-trips
+    rng = np.random.default_rng(3)
+    cnt = rng.integers(0, 5, size=40)
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    val = np.concatenate([np.sort(rng.choice(60, size=c, replace=False)) for c in cnt] + [np.zeros(0, int)]).astype(np.int32)
+    words = lib.ocp_b200_internal_compress_index(40, ip(ptr), ip(val), None, C.byref(regions))
+    assert words >= val.size + 41

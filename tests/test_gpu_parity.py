@@ -476,3 +476,78 @@ def test_streamed_factor_paths_match_oracle(native, monkeypatch, name, horizon, 
     assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
     assert rel_err(x, ox) < REL_SOLUTION
     assert np.allclose(f, of, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,horizon", [("quadrotor", 20), ("quadrotor", 5), ("cartpole", 20)])
+def test_compact_plan_matches_oracle(native, monkeypatch, name, horizon):
+    """The four-CTA/SM throughput kernel (admm_compact_kernel.cuh: stage-periodic index templates, slab-streamed
+    q / l / u / D / E / P, phase-shared buffers) forced onto small batches: same iterates as the oracle, and --
+    with tight tolerances -- through its rho-update refactorisation path (x, z, y parked in the slab)."""
+    monkeypatch.setenv("OCP_B200_PLAN", "compact")
+    prob = native.Problem(name, horizon=horizon)
+    ora = _oracle.OracleProblem(name, horizon=horizon)
+    assert prob.solver.launch_plan()["wide"]["place"] == 4 and prob.solver.launch_plan()["deep"]["place"] == 4
+    B = 3
+    frames, refs = prob.sample_inputs(B, 0xB200 + 17)
+    for alpha, steps, eps in ((0.5, 3, 1e-3), (1.0, 2, 1e-7)):
+        s = prob.get_settings()
+        s.sqp_alpha, s.sqp_step_num = alpha, steps
+        s.eps_abs = s.eps_rel = eps
+        prob.solver.update_settings(s)
+        x0 = np.tile(frames, (1, prob.horizon))
+        x = x0.copy(); f = np.zeros(B); st = np.zeros((B, native.NSTATS))
+        prob.solver.solve_batch(frames, refs, prob.lbx, prob.ubx, prob.lbg, prob.ubg, x, f, st)
+        ora.set_schedule(steps, alpha)
+        ora.set_qp_settings(_oracle.settings_from_b200(s))
+        ox, of, ost = ora.solve_batch(frames, refs, x0=x0)
+        assert np.isfinite(ox).all()
+        assert np.array_equal(st[:, native.STAT["admm_iters"]], ost[:, 2])
+        assert np.array_equal(st[:, native.STAT["rho_updates"]], ost[:, 7])
+        assert np.array_equal(st[:, native.STAT["qp_status"]], ost[:, 0])
+        assert rel_err(x, ox) < REL_SOLUTION
+        assert np.allclose(f, of, rtol=1e-6, atol=1e-9)
+    if name == "quadrotor" and horizon == 20:
+        assert st[:, native.STAT["rho_updates"]].sum() >= 1      # the refactorisation path ran
+
+
+def test_compact_plan_qp_level(native, monkeypatch):
+    """QP-level entry points on the compact kernel: primal / dual solutions, residuals, the check trace, an
+    infeasible QP (certificate -> NaN solution) and inconsistent bounds (zero step)."""
+    monkeypatch.setenv("OCP_B200_PLAN", "compact")
+    prob = native.Problem("quadrotor")
+    ora = _oracle.OracleProblem("quadrotor")
+    hv, q, av, l, u = _qp_case(prob, ora, 21)
+    s = prob.get_settings()
+    s.eps_abs = s.eps_rel = 1e-7
+    prob.solver.update_settings(s)
+    x, y, info = prob.solver.qp_solve_batch(hv, q, av, l, u)
+    sv = _oracle.settings_from_b200(s)
+    for b in range(hv.shape[0]):
+        ox, oy, oinfo, otrace = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[b], q[b], prob.a_colptr,
+                                                 prob.a_rowidx, av[b], l[b], u[b], settings=sv)
+        assert info[b, native.INFO["status"]] == oinfo[0] == native.QP_SOLVED
+        assert info[b, native.INFO["iters"]] == oinfo[1]
+        assert info[b, native.INFO["rho_updates"]] == oinfo[6]
+        assert rel_err(x[b], ox) < REL_SOLUTION and rel_err(y[b], oy) < REL_SOLUTION
+    trace, tx, ty = prob.solver.admm_trace(hv[0], q[0], av[0], l[0], u[0])
+    ox, oy, oinfo, otrace = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[0], q[0], prob.a_colptr,
+                                             prob.a_rowidx, av[0], l[0], u[0], settings=sv)
+    assert len(trace) == len(otrace) > 1 and np.array_equal(trace[:, 0], otrace[:, 0])
+    assert np.allclose(trace[:, 3], otrace[:, 3], rtol=1e-6)
+    assert np.allclose(trace[:, 1], otrace[:, 1], rtol=1e-4, atol=1e-10)
+    # primal infeasible: the whole first frame is pinned and the first defect row fixes the roll angle of stage 1
+    # (up to its residual), so a bound row that wants that angle in [5, 6] cannot hold
+    l2, u2 = l.copy(), u.copy()
+    row = prob.np_ + prob.nf + 3
+    l2[:, row], u2[:, row] = 5.0, 6.0
+    x2, y2, info2 = prob.solver.qp_solve_batch(hv, q, av, l2, u2)
+    for b in range(hv.shape[0]):
+        ox, oy, oinfo, _ = _oracle.qp_solve(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, hv[b], q[b], prob.a_colptr,
+                                            prob.a_rowidx, av[b], l2[b], u2[b], settings=sv)
+        assert info2[b, native.INFO["status"]] == oinfo[0] == native.QP_PRIMAL_INFEASIBLE
+        assert info2[b, native.INFO["iters"]] == oinfo[1]
+        assert np.array_equal(np.isnan(x2[b]), np.isnan(ox))
+    # l > u: osqp_setup refuses, zero step
+    l3 = l.copy(); l3[:, 5] = u[:, 5] + 1.0
+    x3, y3, info3 = prob.solver.qp_solve_batch(hv, q, av, l3, u)
+    assert (info3[:, native.INFO["status"]] == native.QP_UNSOLVED).all() and (x3 == 0).all()
