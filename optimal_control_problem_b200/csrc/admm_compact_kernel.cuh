@@ -40,10 +40,12 @@ struct Layout {
   int s_stride, sp_stride, stage_stride;
   // slab
   size_t dinv, lsub, lp, q, l, u, D, E, pval, dx, dy, an, cn, sx, sz, sy, slab_doubles;
-  bool ok;
+  bool ok, q_smem, lu_smem;
 };
 
-__host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_words) {
+// flags: bit 0 = q in shared memory, bit 1 = l and u in shared memory (otherwise streamed from the slab)
+constexpr int kQInSmem = 1, kLuInSmem = 2;
+__host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_words, int flags) {
   auto ev = [](size_t v) { return (v + 1) & ~size_t(1); };
   const size_t n = ev(P.n), m = ev(P.m), np = P.tri_np, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb;
   Layout L{};
@@ -67,12 +69,20 @@ __host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_wor
   L.xp = o; o += ev(np + 2);
   L.piv = o; o += 64;
   L.arena = o; o += ev((size_t(arena_words) + 1) / 2);
+  size_t qs = 0, ls = 0, us = 0;
+  if (flags & kQInSmem) { qs = o; o += n; }
+  if (flags & kLuInSmem) { ls = o; o += m; us = o; o += m; }
   L.smem_doubles = o;
   size_t g = 0;
   L.dinv = g; g += nb * bs * ld; L.lsub = g; g += nb * bs * ld; L.lp = g; g += ev(np * nb * bs);
-  L.q = g; g += n; L.l = g; g += m; L.u = g; g += m; L.D = g; g += n; L.E = g; g += m;
+  L.q_smem = (flags & kQInSmem) != 0; L.lu_smem = (flags & kLuInSmem) != 0;
+  if (L.q_smem) L.q = qs; else { L.q = g; g += n; }
+  if (L.lu_smem) { L.l = ls; L.u = us; } else { L.l = g; g += m; L.u = g; g += m; }
+  L.D = g; g += n; L.E = g; g += m;
   L.pval = g; g += ev(P.nnz_p); L.dx = g; g += n; L.dy = g; g += m; L.an = g; g += n; L.cn = g; g += n;
-  L.sx = g; g += n; L.sz = g; g += m; L.sy = g; g += m;
+  // parking space of a refactorisation: dx, dy and the Ruiz by-products are dead at that point
+  L.sx = L.dx; L.sz = L.dy;
+  if (2 * n >= m) L.sy = L.an; else { L.sy = g; g += m; }
   L.slab_doubles = (g + 15) & ~size_t(15);
   return L;
 }
@@ -137,12 +147,13 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
     const double* qv = A.q + size_t(inst) * A.ld_n;
     const double* lv = A.l + size_t(inst) * A.ld_m;
     const double* uv = A.u + size_t(inst) * A.ld_m;
-    for (int k = tid; k < P.nnz_a; k += T) W.Aval[k] = av[k];
-    for (int k = tid; k < P.nnz_p; k += T) { const int s = P.p_src[k]; X.psm[k] = s >= 0 ? hv[s] : 0.0; }
-    for (int j = tid; j < n; j += T) { W.q[j] = qv[j]; W.D[j] = 1.0; }
+    // the inputs are read once: streaming loads (evict-first), they must not displace the slabs in L2
+    for (int k = tid; k < P.nnz_a; k += T) W.Aval[k] = __ldcs(av + k);
+    for (int k = tid; k < P.nnz_p; k += T) { const int s = P.p_src[k]; X.psm[k] = s >= 0 ? __ldcs(hv + s) : 0.0; }
+    for (int j = tid; j < n; j += T) { W.q[j] = __ldcs(qv + j); W.D[j] = 1.0; }
     double bad[1] = {0.0};
     for (int i = tid; i < m; i += T) {
-      const double lo = lv[i], hi = uv[i];
+      const double lo = __ldcs(lv + i), hi = __ldcs(uv + i);
       if (lo > hi) bad[0] = 1.0;
       W.l[i] = fmax(lo, -kInfty);
       W.u[i] = fmin(hi, kInfty);
@@ -447,6 +458,8 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
         for (int j = tid; j < n; j += T) X.sx[j] = W.x[j];
         for (int i = tid; i < m; i += T) { X.sz[i] = W.z[i]; X.sy[i] = W.y[i]; }
         __syncthreads();
+        // (inlined a second time on purpose: an out-of-line copy shared with the set-up was measured slower,
+        // 9.6 -> 9.8 ms per launch with P and W passed by value, 11.7 ms by reference)
         direct::tri_assemble_program(P, W, rv, sigma);
         direct::tri_factor_twisted<BS>(P, W);
         for (int j = tid; j < n; j += T) W.x[j] = X.sx[j];
@@ -476,13 +489,13 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
 // persistent kernel: CTAs pull instances from A.counter
 template <int BS, int kThreads, int kBlocksPerSm>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSm)
-admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_settings S, const SolveArgs A) {
+admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_settings S, const SolveArgs A, const int layout_flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red_buf[2 * (kThreads / 32) * kRedWidth];
   __shared__ int s_inst;
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* gl = A.slab + size_t(blockIdx.x) * A.slab_doubles;
-  const Layout L = make_layout(P, C.arena_words);
+  const Layout L = make_layout(P, C.arena_words, layout_flags);
   Work W{};
   W.b = sm + L.b; W.x = sm + L.x; W.w = sm + L.w; W.z = sm + L.z; W.y = sm + L.y;
   W.Aval = sm + L.aval; W.ctype = reinterpret_cast<signed char*>(sm + L.ctype);
@@ -491,7 +504,8 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
   W.s_stride = L.s_stride; W.sp_stride = L.sp_stride; W.stage_stride = L.stage_stride;
   W.ring_bar = nullptr; W.ring_phase = nullptr; W.ring_slots = 0;
   W.Dinv = gl + L.dinv; W.Lsub = gl + L.lsub; W.Lp = gl + L.lp;
-  W.q = gl + L.q; W.l = gl + L.l; W.u = gl + L.u; W.D = gl + L.D; W.E = gl + L.E;
+  W.q = (L.q_smem ? sm : gl) + L.q; W.l = (L.lu_smem ? sm : gl) + L.l; W.u = (L.lu_smem ? sm : gl) + L.u;
+  W.D = gl + L.D; W.E = gl + L.E;
   W.Pval = gl + L.pval; W.dx = gl + L.dx; W.dy = gl + L.dy;
   W.idx = nullptr; W.phase = nullptr;
   uint32_t* ar = reinterpret_cast<uint32_t*>(sm + L.arena);

@@ -112,6 +112,7 @@ struct ocp_b200_solver {
   DevBuf<uint32_t> d_arena;
   ocpb200::CompactIdx cidx{};
   int compact_ok = 0;
+  int compact_variant = 0, compact_flags = 0;   // shape (128x4 / 192x3) and which streamed vectors moved into shared memory
   // stage library
   void* lib = nullptr;
   model_assemble_fn assemble = nullptr;
@@ -473,24 +474,37 @@ int plan_launch(ocp_b200_solver* s) {
     else if (env && !std::strcmp(env, "big") && fits_big) deep = wide = 3;
     RC_TRY(make_plan(deep, s->deep));
     RC_TRY(make_plan(wide, s->wide));
-    // compact throughput plan (admm_compact_kernel.cuh): 128 threads, index templates, streamed slab
-    // vectors -- taken when it puts more CTAs on an SM than the plan above (OCP_B200_PLAN=compact forces it,
-    // any other value of OCP_B200_PLAN keeps it out)
+    // compact throughput plan (admm_compact_kernel.cuh): index templates, streamed slab vectors, three or four
+    // CTAs per SM -- taken when it keeps more threads resident than the plan above (OCP_B200_PLAN=compact forces it,
+    // any other value of OCP_B200_PLAN keeps it out).  OCP_B200_COMPACT_VARIANT = 128x4 | 192x3 picks the shape;
+    // q, then l and u, move from the slab into shared memory while the residency target still holds.
+    s->compact_variant = 0; s->compact_flags = 0;
     if (s->compact_ok && (P.tri_bs == 16 || P.tri_bs == 20) && P.tri_ld == P.tri_bs + 2 && (!env || !std::strcmp(env, "compact"))) {
       namespace K = ocpb200::compact;
-      size_t sm_d = 0, sl_d = 0;
-      bool lay_ok = false;
-      K::plan_sizes(P, s->cidx.arena_words, &sm_d, &sl_d, &lay_ok);
+      int variant = 1;   // measured on the H = 20 quadrotor: both shapes 9.6 ms per launch; 192x3 keeps 64 MB of slabs in L2, 128x4 91 MB
+      if (const char* e = std::getenv("OCP_B200_COMPACT_VARIANT")) variant = !std::strcmp(e, "128x4") ? 0 : 1;
+      const int target = variant == 0 ? 4 : 3;
       D::KernelInfo kc{};
-      CUDA_TRY(K::kernel_info(P.tri_bs, &kc));
-      if (lay_ok && sm_d * sizeof(double) + kc.static_smem <= size_t(max_optin)) {
-        CUDA_TRY(K::set_max_dynamic_smem(P.tri_bs, max_optin - kc.static_smem));
-        int occ = 1;
-        CUDA_TRY(K::occupancy(P.tri_bs, static_cast<int>(sm_d * sizeof(double)), &occ));
+      CUDA_TRY(K::kernel_info(P.tri_bs, variant, &kc));
+      CUDA_TRY(K::set_max_dynamic_smem(P.tri_bs, variant, max_optin - kc.static_smem));
+      int best_flags = -1, best_occ = 0;
+      size_t best_sm = 0, best_sl = 0;
+      for (int flags : {3, 1, 0}) {   // most shared memory first
+        size_t sm_d = 0, sl_d = 0;
+        bool lay_ok = false;
+        K::plan_sizes(P, s->cidx.arena_words, flags, &sm_d, &sl_d, &lay_ok);
+        if (!lay_ok || sm_d * sizeof(double) + kc.static_smem > size_t(max_optin)) continue;
+        int occ = 0;
+        CUDA_TRY(K::occupancy(P.tri_bs, variant, static_cast<int>(sm_d * sizeof(double)), &occ));
+        if (occ > best_occ && best_occ < target) { best_occ = occ; best_flags = flags; best_sm = sm_d; best_sl = sl_d; }
+      }
+      if (best_flags >= 0) {
+        int occ = std::min(best_occ, target);
         if (const char* cap = std::getenv("OCP_B200_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, std::atoi(cap)));
-        if (occ * kc.threads > (s->wide.max_ctas / s->num_sms) * s->wide.threads || (env && occ >= 1)) {
-          s->wide.place = 4; s->wide.threads = kc.threads; s->wide.smem_bytes = static_cast<int>(sm_d * sizeof(double));
-          s->wide.smem_mask = 0; s->wide.slab_doubles = sl_d; s->wide.max_ctas = occ * s->num_sms;
+        if (occ * kc.threads > (s->wide.max_ctas / s->num_sms) * s->wide.threads || env) {
+          s->wide.place = 4; s->wide.threads = kc.threads; s->wide.smem_bytes = static_cast<int>(best_sm * sizeof(double));
+          s->wide.smem_mask = 0; s->wide.slab_doubles = best_sl; s->wide.max_ctas = occ * s->num_sms;
+          s->compact_variant = variant; s->compact_flags = best_flags;
           if (env) s->deep = s->wide;
         }
       }
@@ -588,7 +602,7 @@ int launch_admm(ocp_b200_solver* s, SolveArgs& A, cudaStream_t st) {
       A.slab = s->slab.p;
     }
     if (L.place == 4)
-      CUDA_TRY(ocpb200::compact::launch(s->pat.tri_bs, grid, L.smem_bytes, st, s->pat, s->cidx, s->settings, A));
+      CUDA_TRY(ocpb200::compact::launch(s->pat.tri_bs, s->compact_variant, grid, L.smem_bytes, st, s->pat, s->cidx, s->settings, A, s->compact_flags));
     else
       CUDA_TRY(ocpb200::direct::launch(L.place, grid, L.smem_bytes, st, s->pat, s->settings, A, L.smem_mask));
   } else if (s->resident) {
