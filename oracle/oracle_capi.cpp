@@ -240,6 +240,21 @@ int oracle_kat_solve(int id, int step_num, double alpha, int use_float, double* 
   ORACLE_CATCH
 }
 
+// CCS patterns (casadi-lite) of the local system of test/test.cpp case `id`: sizes = {n, m, nnz_h, nnz_a};
+// the index arrays are written when non-null (hp / ap: n + 1 entries, hi / ai: nnz entries, at most 64 each).
+int oracle_kat_patterns(int id, int* sizes, int* hp, int* hi, int* ap, int* ai) {
+  ORACLE_TRY
+  ocp_problems::KatCase kc = ocp_problems::make_kat(id);
+  SqpReference<double> ref(kc.nlp, 1, 1.0);
+  sizes[0] = ref.n(); sizes[1] = ref.m();
+  sizes[2] = static_cast<int>(ref.h_rowidx().size()); sizes[3] = static_cast<int>(ref.a_rowidx().size());
+  if (hp) std::copy(ref.h_colptr().begin(), ref.h_colptr().end(), hp);
+  if (hi) std::copy(ref.h_rowidx().begin(), ref.h_rowidx().end(), hi);
+  if (ap) std::copy(ref.a_colptr().begin(), ref.a_colptr().end(), ap);
+  if (ai) std::copy(ref.a_rowidx().begin(), ref.a_rowidx().end(), ai);
+  ORACLE_CATCH
+}
+
 int oracle_kat_expected(int id, double* x_out, int* n_out) {
   ORACLE_TRY
   ocp_problems::KatCase kc = ocp_problems::make_kat(id);

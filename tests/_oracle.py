@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
                                       dptr, dptr, dptr, dptr, C.c_int, iptr, C.c_int]
         L.oracle_kat_solve.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, dptr, iptr, dptr, dptr]
         L.oracle_kat_expected.argtypes = [C.c_int, dptr, iptr]
+        L.oracle_kat_patterns.argtypes = [C.c_int, iptr, iptr, iptr, iptr, iptr]
         L.oracle_sample_inputs.argtypes = [C.c_char_p, C.c_int, C.c_ulonglong, dptr, dptr]
         _lib = L
     return _lib
@@ -164,6 +165,15 @@ def kat_solve(case: int, step_num: int = 1, alpha: float = 1.0, use_float: bool 
     x = np.zeros(8); n = C.c_int(0); f = np.zeros(1); st = np.zeros(12)
     _check(lib().oracle_kat_solve(case, step_num, alpha, int(use_float), _dp(x), C.byref(n), _dp(f), _dp(st)))
     return x[: n.value].copy(), float(f[0]), st
+
+
+def kat_patterns(case: int):
+    """(h_colptr, h_rowidx, a_colptr, a_rowidx) of the local system of test/test.cpp case `case` as casadi-lite builds it."""
+    sizes = (C.c_int * 4)()
+    hp = np.zeros(64, np.int32); hi = np.zeros(64, np.int32); ap = np.zeros(64, np.int32); ai = np.zeros(64, np.int32)
+    _check(lib().oracle_kat_patterns(case, sizes, _ip(hp), _ip(hi), _ip(ap), _ip(ai)))
+    n, m, nh, na = list(sizes)
+    return hp[:n + 1].copy(), hi[:nh].copy(), ap[:n + 1].copy(), ai[:na].copy()
 
 
 def kat_expected(case: int) -> np.ndarray:
