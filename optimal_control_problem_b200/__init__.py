@@ -473,6 +473,10 @@ class MpcLoop:
         self.problem, self.B = problem, int(batch)
         self.solver = problem.solver
         self.device = torch.device(device if device is not None else "cuda:0")
+        # the solver handle of a Problem lives on device 0 (SQPOptimizationSolver's default): tensors and the
+        # stream of another GPU must not be handed to its kernels
+        if self.device.type != "cuda" or (self.device.index or 0) != 0:
+            raise ValueError(f"MpcLoop: the solver of this Problem is on cuda:0, got device {self.device}")
         f64 = dict(dtype=torch.float64, device=self.device)
         self.x = torch.zeros((self.B, problem.N), **f64)
         self.f = torch.zeros(self.B, **f64)

@@ -268,7 +268,8 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
   for (int i = tid; i < m; i += T) { W.z[i] = 0.0; W.y[i] = 0.0; W.w[i] = 0.0; }
   __syncthreads();
 
-  const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : 4 * S.check_termination;
+  // OSQP without wall-clock profiling: 4 x check_termination, or ADAPTIVE_RHO_FIXED = 100 iterations when checks are off
+  const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : (S.check_termination > 0 ? 4 * S.check_termination : 100);
   int status = OCP_B200_QP_UNSOLVED, iter = 0, solves = 0, rho_updates = 0, checks = 0, n_trace = 0;
   double prim_res = 0.0, dual_res = 0.0;
   bool done = false;

@@ -1106,7 +1106,8 @@ __device__ inline void solve_instance(const PatternDev& P, const ocp_b200_settin
   factor_dispatch<kPlace>(P, W);
   clk.lap(OCP_B200_PHASE_FACTOR);
 
-  const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : 4 * S.check_termination;
+  // OSQP without wall-clock profiling: 4 x check_termination, or ADAPTIVE_RHO_FIXED = 100 iterations when checks are off
+  const int rho_interval = S.adaptive_rho_interval > 0 ? S.adaptive_rho_interval : (S.check_termination > 0 ? 4 * S.check_termination : 100);
   int status = OCP_B200_QP_UNSOLVED, iter = 0, solves = 0, rho_updates = 0, checks = 0, n_trace = 0;
   double prim_res = 0.0, dual_res = 0.0;
   bool done = false;

@@ -61,6 +61,21 @@ int fail(int code, const std::string& msg) {
 
 #define RC_TRY(expr) do { int rc_ = (expr); if (rc_ != OCP_B200_OK) return rc_; } while (0)
 
+// Every entry point works on the handle's device and puts the caller's current device back when it returns
+// (the caller may be a torch process whose current device is another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t enter(int dev) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != dev) { e = cudaSetDevice(dev); changed = e == cudaSuccess; }
+    return e;
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(dev) DeviceGuard device_guard_; CUDA_TRY(device_guard_.enter(dev))
+
 using ocpb200::idx_t;
 using ocpb200::PatternDev;
 using ocpb200::SolveArgs;
@@ -575,6 +590,25 @@ struct ProfScope {
   ocp_b200_solver* s; cudaStream_t st; cudaEvent_t stop = nullptr;
   ProfScope(ocp_b200_solver* s_, int kind, cudaStream_t st_) : s(s_), st(st_) {
     if (!s->profiling) return;
+    // bounded: pairs that have completed are folded into the totals; with kMaxPending still in flight this
+    // launch simply goes untimed (nothing blocks here)
+    constexpr size_t kMaxPending = 4096;
+    if (s->ev_kind.size() >= kMaxPending) {
+      size_t keep = 0;
+      for (size_t k = 0; k < s->ev_kind.size(); ++k) {
+        cudaEvent_t ea = s->ev[2 * k], eb = s->ev[2 * k + 1];
+        float t = 0.f;
+        if (cudaEventQuery(eb) == cudaSuccess && cudaEventElapsedTime(&t, ea, eb) == cudaSuccess) {
+          s->prof_ms[s->ev_kind[k]] += t; s->prof_count[s->ev_kind[k]]++;
+          cudaEventDestroy(ea); cudaEventDestroy(eb);
+        } else {
+          s->ev[2 * keep] = ea; s->ev[2 * keep + 1] = eb; s->ev_kind[keep] = s->ev_kind[k]; ++keep;
+        }
+      }
+      cudaGetLastError();
+      s->ev.resize(2 * keep); s->ev_kind.resize(keep);
+      if (keep >= kMaxPending) return;
+    }
     cudaEvent_t a, b;
     if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
     s->ev.push_back(a); s->ev.push_back(b); s->ev_kind.push_back(kind);
@@ -693,10 +727,14 @@ int ocp_b200_create(const ocp_b200_problem_desc* d, const ocp_b200_settings* set
   ocp_b200_settings dflt;
   if (!settings) { ocp_b200_default_settings(&dflt); settings = &dflt; }
   RC_TRY(check_settings(settings));
-  if (d->np < 0 || d->nf <= 0 || d->horizon <= 0 || d->ng < 0 || !d->h_colptr || !d->a_colptr ||
+  // a QP-only handle (no stage library; CuCaQP) may have FEWER constraint rows than variables: ng = m - n < 0.
+  // The OCP entry points need the identity rows of c = [p; x; g], i.e. ng >= 0.
+  const bool qp_only = !(d->model_library && d->model_library[0]);
+  if (d->np < 0 || d->nf <= 0 || d->horizon <= 0 || (d->ng < 0 && !qp_only) || !d->h_colptr || !d->a_colptr ||
       (d->nnz_h > 0 && !d->h_rowidx) || (d->nnz_a > 0 && !d->a_rowidx))
     return fail(OCP_B200_ERR_INVALID, "bad problem description");
   const long long n = (long long)d->np + (long long)d->nf * d->horizon, m = n + d->ng;
+  if (m < 1) return fail(OCP_B200_ERR_INVALID, "a QP needs at least one constraint row (the reference's OSQP set-up rejects m = 0 as well)");
   if (n <= 0 || m > 65534) return fail(OCP_B200_ERR_UNSUPPORTED, "problem too large for 16-bit index structures");
   if (d->h_colptr[0] != 0 || d->h_colptr[n] != d->nnz_h || d->a_colptr[0] != 0 || d->a_colptr[n] != d->nnz_a)
     return fail(OCP_B200_ERR_INVALID, "column pointers do not match nnz");
@@ -716,7 +754,7 @@ int ocp_b200_create(const ocp_b200_problem_desc* d, const ocp_b200_settings* set
     return fail(OCP_B200_ERR_NO_DEVICE, std::string("no CUDA device (there is no CPU fallback): ") +
                                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (d->device < 0 || d->device >= ndev) return fail(OCP_B200_ERR_INVALID, "device ordinal out of range");
-  CUDA_TRY(cudaSetDevice(d->device));
+  ENTER_DEVICE(d->device);
 
   ocp_b200_solver* s = new (std::nothrow) ocp_b200_solver();
   if (!s) return fail(OCP_B200_ERR_INVALID, "out of host memory");
@@ -748,7 +786,8 @@ int ocp_b200_create(const ocp_b200_problem_desc* d, const ocp_b200_settings* set
 
 int ocp_b200_destroy(ocp_b200_solver* s) {
   if (!s) return OCP_B200_OK;
-  cudaSetDevice(s->device);
+  DeviceGuard device_guard_;
+  device_guard_.enter(s->device);
   if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
   s->d_idx.release(); s->d_int.release(); s->d_kent.release(); s->d_krun.release(); s->d_arena.release();
   DevBuf<double>* bufs[] = {&s->hv, &s->q, &s->av, &s->l, &s->u, &s->solx, &s->soly, &s->info, &s->slab, &s->trace,
@@ -768,7 +807,7 @@ int ocp_b200_update_settings(ocp_b200_solver* s, const ocp_b200_settings* settin
   const int old = s->settings.pcg_precond;
   s->settings = *settings;
   if (old != settings->pcg_precond) {
-    CUDA_TRY(cudaSetDevice(s->device));
+    ENTER_DEVICE(s->device);
     RC_TRY(plan_launch(s));
   }
   return OCP_B200_OK;
@@ -788,7 +827,7 @@ int ocp_b200_solve_batch_device(ocp_b200_solver* s, int B, const double* d_frame
     return fail(OCP_B200_ERR_INVALID, "bad arguments to solve_batch");
   if (B == 0) return OCP_B200_OK;
   if (!s->assemble) return fail(OCP_B200_ERR_MODEL, "this handle has no stage library (QP-only handle)");
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RC_TRY(reserve_qp(s, B));
   CUDA_TRY(s->stats.reserve(size_t(B) * OCP_B200_NSTATS));
@@ -825,7 +864,7 @@ int ocp_b200_shift_iterate_device(ocp_b200_solver* s, int B, double* d_x, void* 
   if (B == 0 || s->N <= s->nf) return OCP_B200_OK;
   const size_t smem = size_t(s->N) * sizeof(double);
   if (smem > 48 * 1024) return fail(OCP_B200_ERR_UNSUPPORTED, "shift_iterate: trajectory longer than 6144 values");
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   ocpb200::shift_iterate_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(s->nf, s->N, d_x);
   CUDA_TRY(cudaGetLastError());
   s->launches++;
@@ -839,7 +878,7 @@ int ocp_b200_solve_batch(ocp_b200_solver* s, int B, const double* frames, const 
   if (B < 0 || (B > 0 && (!x_inout || (s->np > 0 && !p) || !lbx || !ubx || (s->ng > 0 && (!lbg || !ubg)))))
     return fail(OCP_B200_ERR_INVALID, "bad arguments to solve_batch");
   if (B == 0) return OCP_B200_OK;
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   cudaStream_t st = s->stream;
   RC_TRY(upload_problem_inputs(s, B, frames, p, lbx, ubx, lbg, ubg, st));
   CUDA_TRY(s->x.reserve(size_t(B) * s->N));
@@ -861,7 +900,7 @@ int ocp_b200_export_qp(ocp_b200_solver* s, int B, const double* frames, const do
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
   if (B <= 0 || !x || (s->np > 0 && !p) || !lbx || !ubx || (s->ng > 0 && (!lbg || !ubg)))
     return fail(OCP_B200_ERR_INVALID, "bad arguments to export_qp");
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   cudaStream_t st = s->stream;
   RC_TRY(upload_problem_inputs(s, B, frames, p, lbx, ubx, lbg, ubg, st));
   CUDA_TRY(s->x.reserve(size_t(B) * s->N));
@@ -883,7 +922,7 @@ static int qp_solve_common(ocp_b200_solver* s, int B, const double* h_vals, cons
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
   if (B <= 0 || (s->nnz_h > 0 && !h_vals) || !q || !a_vals || !l || !u)
     return fail(OCP_B200_ERR_INVALID, "bad arguments to qp_solve");
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   cudaStream_t st = s->stream;
   RC_TRY(reserve_qp(s, B));
   CUDA_TRY(s->solx.reserve(size_t(B) * s->n));
@@ -943,7 +982,7 @@ int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled) {
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
   s->profiling = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
   if (enabled >= 2) {
-    CUDA_TRY(cudaSetDevice(s->device));
+    ENTER_DEVICE(s->device);
     CUDA_TRY(s->phase.reserve(OCP_B200_NPHASE));
     CUDA_TRY(cudaMemset(s->phase.p, 0, OCP_B200_NPHASE * sizeof(long long)));
   }
@@ -953,7 +992,7 @@ int ocp_b200_set_profiling(ocp_b200_solver* s, int enabled) {
 int ocp_b200_get_phase_cycles(ocp_b200_solver* s, long long* cycles) {
   if (!s || !cycles) return fail(OCP_B200_ERR_INVALID, "solver/cycles is NULL");
   if (!s->phase.p) { for (int k = 0; k < OCP_B200_NPHASE; ++k) cycles[k] = 0; return OCP_B200_OK; }
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(cycles, s->phase.p, OCP_B200_NPHASE * sizeof(long long), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemset(s->phase.p, 0, OCP_B200_NPHASE * sizeof(long long)));
@@ -962,7 +1001,7 @@ int ocp_b200_get_phase_cycles(ocp_b200_solver* s, long long* cycles) {
 
 int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int reset) {
   if (!s) return fail(OCP_B200_ERR_INVALID, "solver is NULL");
-  CUDA_TRY(cudaSetDevice(s->device));
+  ENTER_DEVICE(s->device);
   for (size_t k = 0; k < s->ev_kind.size(); ++k) {
     cudaEvent_t a = s->ev[2 * k], b = s->ev[2 * k + 1];
     CUDA_TRY(cudaEventSynchronize(b));

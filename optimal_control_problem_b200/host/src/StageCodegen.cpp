@@ -547,8 +547,27 @@ extern "C" int ocp_b200_model_objective(int B, const double* x, const double* p,
   return out;
 }
 
+namespace {
+// single-quoted for /bin/sh: the only character that needs care inside '...' is the quote itself
+std::string sh_quote(const std::string& v) {
+  std::string out = "'";
+  for (char c : v) {
+    if (c == '\'') out += "'\\''";
+    else out += c;
+  }
+  return out + "'";
+}
+}  // namespace
+
+// Several processes may build the same model at once (one rank per GPU, each calling genSolver() on a cold
+// cache): every file a build writes carries the pid until it is complete and is then renamed into place, so no
+// process ever reads a half-written source and nvcc never reads a file another rank is rewriting.  The model name
+// becomes part of a file name and of a shell command line: it is restricted to [A-Za-z0-9_], paths are quoted.
 std::string compile(const ModelSource& src, const std::string& name, const std::string& code_dir, bool verbose) {
   namespace fs = std::filesystem;
+  if (name.empty() || name.size() > 64 ||
+      name.find_first_not_of("ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789_") != std::string::npos)
+    throw std::invalid_argument("codegen: problem name '" + name + "' must match [A-Za-z0-9_]{1,64}");
   fs::create_directories(code_dir);
   char hx[32];
   std::snprintf(hx, sizeof(hx), "%016llx", src.hash);
@@ -558,28 +577,37 @@ std::string compile(const ModelSource& src, const std::string& name, const std::
     if (verbose) std::cout << "stage library cached: " << so << std::endl;
     return so;
   }
+  const std::string pid = std::to_string(static_cast<long>(::getpid()));
+  const std::string cu_tmp = stem + ".tmp." + pid + ".cu", so_tmp = so + ".tmp." + pid;
   {
-    std::ofstream f(cu);
-    if (!f.good()) throw std::runtime_error("codegen: cannot write " + cu);
+    std::ofstream f(cu_tmp);
+    if (!f.good()) throw std::runtime_error("codegen: cannot write " + cu_tmp);
     f << src.source;
+    f.close();
+    if (!f.good()) throw std::runtime_error("codegen: short write to " + cu_tmp);
   }
   const char* nvcc_env = std::getenv("OCP_B200_NVCC");
   const std::string nvcc = nvcc_env ? nvcc_env : "nvcc";
-  const std::string tmp = so + ".tmp." + std::to_string(static_cast<long>(::getpid()));
-  const char* extra_env = std::getenv("OCP_B200_NVCC_FLAGS");
+  const char* extra_env = std::getenv("OCP_B200_NVCC_FLAGS");   // trusted: extra compiler flags, split by the shell
   const std::string extra = extra_env ? std::string(" ") + extra_env : std::string();
-  const std::string cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared "
-                          "-Xcompiler -fPIC" + extra + " -I" + include_dir() + " -o " + tmp + " " + cu + " 2>&1";
+  const std::string cmd = sh_quote(nvcc) + " -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared "
+                          "-Xcompiler -fPIC" + extra + " -I" + sh_quote(include_dir()) + " -o " + sh_quote(so_tmp) + " " +
+                          sh_quote(cu_tmp) + " 2>&1";
   if (verbose) std::cout << "compiling stage library: " << cmd << std::endl;
   FILE* pipe = popen(cmd.c_str(), "r");
-  if (!pipe) throw std::runtime_error("codegen: cannot start nvcc");
+  if (!pipe) { std::error_code ec; fs::remove(cu_tmp, ec); throw std::runtime_error("codegen: cannot start nvcc"); }
   std::string log;
   char buf[512];
   while (fgets(buf, sizeof(buf), pipe)) log += buf;
   const int rc = pclose(pipe);
-  if (rc != 0 || !fs::exists(tmp))
-    throw std::runtime_error("codegen: nvcc failed for " + cu + " (exit " + std::to_string(rc) + ")\n" + log);
-  fs::rename(tmp, so);
+  std::error_code ec;
+  if (rc != 0 || !fs::exists(so_tmp)) {
+    fs::rename(cu_tmp, stem + ".failed.cu", ec);   // kept for inspection
+    fs::remove(so_tmp, ec);
+    throw std::runtime_error("codegen: nvcc failed for " + stem + ".failed.cu (exit " + std::to_string(rc) + ")\n" + log);
+  }
+  fs::rename(cu_tmp, cu, ec);      // the source next to the library (same content from every rank)
+  fs::rename(so_tmp, so);          // atomic: a concurrent reader sees the old state or the complete file
   return so;
 }
 

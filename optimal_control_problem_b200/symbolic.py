@@ -212,6 +212,10 @@ class OptimalControlProblem:
 
     def add_vector_cost(self, weights: Sequence[float], cost: SX) -> None:
         w = _f64(weights)
+        # the C++ addVectorCost(std::vector<double>) keeps the reference's exit(-5) on a size mismatch
+        # (OptimalControlProblem.cpp:591); from Python that would kill the interpreter: check here
+        if w.size != cost.size1():
+            raise ValueError(f"weight vector has {w.size} entries, cost vector {cost.size1()}")
         _hcheck(host_lib().ocp_host_scripted_add_vector_cost(self._h, _dp(w), w.size, cost._h))
 
     def add_inequality_constraint(self, name: str, lower, expression: SX, upper) -> None:
@@ -229,7 +233,10 @@ class OptimalControlProblem:
 
     # ---- solver
     def gen_solver(self) -> None:
-        """``OptimalControlProblem::genSolver()`` (CUDA_SQP branch): needs no GPU."""
+        """``OptimalControlProblem::genSolver()`` (CUDA_SQP branch): needs no GPU.  Idempotent: a second
+        call returns without building a second owner of the host handle."""
+        if self._problem is not None:
+            return
         _hcheck(host_lib().ocp_host_scripted_gen_solver(self._h))
         self._problem = Problem._adopt(self.name, self._h)
 

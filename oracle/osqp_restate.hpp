@@ -267,7 +267,8 @@ class OsqpRestated {
   void solve(Real* x_out, Real* y_out) {
     const OsqpSettings& s = settings;
     const Real alpha = Real(s.alpha), sigma = Real(s.sigma);
-    int rho_interval = s.adaptive_rho_interval > 0 ? s.adaptive_rho_interval : 4 * s.check_termination;
+    int rho_interval = s.adaptive_rho_interval > 0 ? s.adaptive_rho_interval
+                                                    : (s.check_termination > 0 ? 4 * s.check_termination : 100);   // ADAPTIVE_RHO_FIXED
     int iter = 0;
     bool exited = false;
     for (iter = 1; iter <= s.max_iter; ++iter) {

@@ -384,6 +384,27 @@ def test_cucaqp_class_on_general_patterns(native, n, m_extra):
     assert rel_err(y, oy) < REL_SOLUTION
 
 
+def test_cucaqp_fewer_constraints_than_variables(native):
+    """The reference accepts any m > 0 (CuCaQP.cpp:22-41); a QP with m < n has no identity block at all."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(77)
+    n, m = 14, 5
+    M = rng.standard_normal((n, n)) * (rng.random((n, n)) < 0.4)
+    S = sp.csc_matrix(M @ M.T + n * np.eye(n)); S.sort_indices()
+    G = sp.csc_matrix(rng.standard_normal((m, n)) * (rng.random((m, n)) < 0.6)); G.sort_indices()
+    xf = rng.standard_normal(n)
+    l = G @ xf - rng.random(m); u = G @ xf + rng.random(m)
+    l[0] = u[0]
+    q = rng.standard_normal(n)
+    args = (n, m, S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data, q, G.indptr.astype(np.int32),
+            G.indices.astype(np.int32), G.data, l, u)
+    x, y, info = native.cucaqp_solve(*args, eps_abs=1e-7, eps_rel=1e-7)
+    ox, oy, oinfo, _ = _oracle.qp_solve(*args, settings=_oracle.settings_vector(eps_abs=1e-7, eps_rel=1e-7))
+    assert info[native.INFO["status"]] == oinfo[0] == native.QP_SOLVED
+    assert info[native.INFO["iters"]] == oinfo[1]
+    assert rel_err(x, ox) < REL_SOLUTION and rel_err(y, oy) < REL_SOLUTION
+
+
 def test_inconsistent_bounds_give_a_zero_step(problems, native):
     """lbx > ubx on one variable: osqp_setup rejects the QP (validate_data); the reference ignores
     the failure (SQPOptimizationSolver.cpp:155-157) -- restated as a zero step on both sides."""
