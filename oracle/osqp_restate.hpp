@@ -167,49 +167,94 @@ struct Ldl {
   }
 };
 
-// Greedy minimum-degree ordering on the pattern of a symmetric matrix given by its upper
-// triangle.  (Upstream uses SuiteSparse AMD; any fill-reducing ordering leaves the ADMM
-// iterates unchanged up to rounding.)  Bitset adjacency, exact external degree.
+// Fill-reducing ordering of a symmetric matrix given by its upper triangle: approximate minimum degree on
+// the quotient graph (Amestoy, Davis, Duff, "An approximate minimum degree ordering algorithm", SIMAX 1996 --
+// the algorithm behind SuiteSparse AMD, which upstream OSQP calls through QDLDL's interface).  Eliminated
+// variables become elements; a variable's degree is bounded by
+//     d_i = min(n - k,  d_i + |L_p \ i|,  |A_i \ i| + |L_p \ i| + sum_{e in E_i \ p} |L_e \ L_p|)
+// with |L_e \ L_p| obtained for all elements at once (the w(e) pass); elements whose variables all lie in
+// L_p are absorbed.  No supervariables / mass elimination: the KKT systems here have ~10^3 rows.  Any
+// fill-reducing ordering leaves the ADMM iterates unchanged up to rounding; what this buys over the exact
+// greedy minimum degree that round 1 used is set-up TIME (the CPU baseline re-runs it every SQP step, as the
+// reference does: CuCaQP.cpp:273-276).
 inline std::vector<int> min_degree_order(int n, const std::vector<int>& Ap, const std::vector<int>& Ai) {
-  const int W = (n + 63) / 64;
-  std::vector<uint64_t> adj(static_cast<size_t>(n) * W, 0);
-  auto set = [&](int a, int b) { adj[static_cast<size_t>(a) * W + (b >> 6)] |= (uint64_t(1) << (b & 63)); };
+  // the lists keep their capacity from call to call (one set per thread): the ordering is re-run for every QP
+  struct Lists { std::vector<std::vector<int>> A, E, L, bucket; };
+  static thread_local Lists ws;
+  auto reset = [n](std::vector<std::vector<int>>& v, size_t count) {
+    if (v.size() < count) v.resize(count);
+    for (size_t i = 0; i < count; ++i) v[i].clear();
+    (void)n;
+  };
+  reset(ws.A, n); reset(ws.E, n); reset(ws.L, n); reset(ws.bucket, size_t(n) + 1);
+  std::vector<std::vector<int>>&A = ws.A, &E = ws.E, &L = ws.L, &bucket = ws.bucket;
   for (int j = 0; j < n; ++j)
     for (int q = Ap[j]; q < Ap[j + 1]; ++q) {
-      int i = Ai[q];
-      if (i != j) { set(i, j); set(j, i); }
+      const int i = Ai[q];
+      if (i != j) { A[i].push_back(j); A[j].push_back(i); }
     }
-  std::vector<int> deg(n), perm;
-  std::vector<char> done(n, 0);
-  auto count = [&](int v) {
-    int c = 0;
-    const uint64_t* r = &adj[static_cast<size_t>(v) * W];
-    for (int w = 0; w < W; ++w) c += __builtin_popcountll(r[w]);
-    return c;
-  };
-  for (int v = 0; v < n; ++v) deg[v] = count(v);
+  std::vector<int> deg(n), stamp(n, -1), wst(n, -1), w(n, 0), perm;
+  std::vector<char> elim(n, 0), absorbed(n, 0);
+  for (int v = 0; v < n; ++v) {
+    std::sort(A[v].begin(), A[v].end());
+    A[v].erase(std::unique(A[v].begin(), A[v].end()), A[v].end());
+    deg[v] = static_cast<int>(A[v].size());
+    bucket[deg[v]].push_back(v);
+  }
   perm.reserve(n);
-  std::vector<int> nbr;
-  for (int step = 0; step < n; ++step) {
-    int best = -1;
-    for (int v = 0; v < n; ++v)
-      if (!done[v] && (best < 0 || deg[v] < deg[best])) best = v;
-    perm.push_back(best);
-    done[best] = 1;
-    uint64_t* rb = &adj[static_cast<size_t>(best) * W];
-    nbr.clear();
-    for (int w = 0; w < W; ++w) {
-      uint64_t bits = rb[w];
-      while (bits) { int b = __builtin_ctzll(bits); bits &= bits - 1; nbr.push_back(w * 64 + b); }
+  std::vector<int> Lp;
+  int mindeg = 0;
+  for (int k = 0; k < n; ++k) {
+    int p = -1;
+    while (p < 0) {
+      while (mindeg <= n && bucket[mindeg].empty()) ++mindeg;
+      const int c = bucket[mindeg].back();
+      bucket[mindeg].pop_back();
+      if (!elim[c] && deg[c] == mindeg) p = c;   // stale entries (degree changed, already eliminated) are skipped
     }
-    for (int v : nbr) {
-      uint64_t* rv = &adj[static_cast<size_t>(v) * W];
-      for (int w = 0; w < W; ++w) rv[w] |= rb[w];
-      rv[v >> 6] &= ~(uint64_t(1) << (v & 63));
-      rv[best >> 6] &= ~(uint64_t(1) << (best & 63));
-      deg[v] = count(v);
+    // L_p = (A_p  u  union of L_e, e in E_p) \ p ; the elements of E_p are absorbed into p
+    stamp[p] = k;
+    Lp.clear();
+    for (int i : A[p]) if (!elim[i] && stamp[i] != k) { stamp[i] = k; Lp.push_back(i); }
+    for (int e : E[p]) {
+      if (absorbed[e]) continue;
+      for (int i : L[e]) if (!elim[i] && stamp[i] != k) { stamp[i] = k; Lp.push_back(i); }
+      absorbed[e] = 1;
+      L[e].clear();
     }
-    for (int w = 0; w < W; ++w) rb[w] = 0;
+    elim[p] = 1;
+    perm.push_back(p);
+    A[p].clear();
+    E[p].clear();
+    // w(e) = |L_e \ L_p| for every element adjacent to a variable of L_p
+    for (int i : Lp)
+      for (int e : E[i]) {
+        if (absorbed[e]) continue;
+        if (wst[e] != k) { wst[e] = k; w[e] = static_cast<int>(L[e].size()); }
+        --w[e];
+      }
+    const int lp = static_cast<int>(Lp.size());
+    for (int i : Lp) {
+      // A_i loses what L_p now covers; E_i loses absorbed elements (aggressively: those inside L_p) and gains p
+      size_t o = 0;
+      for (int j : A[i]) if (!elim[j] && stamp[j] != k) A[i][o++] = j;
+      A[i].resize(o);
+      long d = static_cast<long>(o) + (lp - 1);
+      o = 0;
+      for (int e : E[i]) {
+        if (absorbed[e]) continue;
+        if (w[e] == 0) { absorbed[e] = 1; L[e].clear(); continue; }
+        E[i][o++] = e;
+        d += w[e];
+      }
+      E[i].resize(o);
+      E[i].push_back(p);
+      d = std::min<long>(d, std::min<long>(n - k - 1, static_cast<long>(deg[i]) + lp - 1));
+      deg[i] = static_cast<int>(std::max<long>(d, 0));
+      bucket[deg[i]].push_back(i);
+      if (deg[i] < mindeg) mindeg = deg[i];
+    }
+    L[p] = Lp;
   }
   return perm;
 }
