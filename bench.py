@@ -11,8 +11,11 @@ iterate x=0 so that all steps do identical work.
 
   value   solves/s, whole job, inputs resident in HBM, CUDA events around ocp_b200_solve_batch_device
   e2e     same through ocp_b200_solve_batch with pinned HOST buffers (H2D + D2H inside the timed region)
-  roofline  admm_solve_kernel: algorithmic bytes (SURVEY.md §8d / DESIGN.md) from the per-instance
-            ADMM / PCG / check counts in the stats buffer, over its CUDA-event time
+  roofline  the ADMM kernel: `frac` = SURVEY.md §8d's streaming byte count (with the iteration / solve / check counts
+            of the stats buffer) over its CUDA-event time and the measured HBM peak -- an EFFECTIVE rate: the kernel keeps
+            its state on chip and in L2 and is bound by dependent-instruction latency (frac_dram, counters alongside)
+  secondary  with 2 or more GPUs (or --secondary): BASELINE.json configs[3] / [4] at their stated TOTAL sizes, split over
+            the ranks (strong scaling), one timed step each
   cpu_baseline  the oracle (restated reference CPU path) on the host cores, bounded sample
 
 `--impl reference` times the oracle alone (rank 0 only).  torch is used for device memory,
@@ -76,6 +79,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="solves in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-solves", type=int, default=50)
+    ap.add_argument("--secondary", default="auto", choices=["auto", "on", "off"],
+                    help="bounded pass over BASELINE.json configs[3]/[4] at their stated total sizes (auto: with >= 2 GPUs)")
     return ap.parse_args()
 
 
@@ -212,28 +217,84 @@ class ClockSampler:
 # the B200 arm
 # ---------------------------------------------------------------------------------------------
 def algorithmic_bytes(dims, nnz_pu, stats, ocp, direct=None):
-    """Bytes one batched solve (all its SQP steps) has to move if every operand of every
-    operation is streamed once (no credit for shared-memory residency), from the per-instance
-    iteration counts in the stats buffer.  PCG kernel: SURVEY.md §8d.  Direct kernel
-    (DESIGN.md §5): per ADMM iteration the rhs build and the fused update read A once each,
-    the block-tridiagonal solve reads D^-1 once and L, L_p twice (forward + backward sweep)."""
+    """SURVEY.md 8(d), as written: bytes one batched solve (all its SQP steps) moves if every operand of every operation
+    is streamed once (no credit for shared-memory residency), with the ACTUAL counts of the stats buffer:
+        bytes_admm(K) = 8 [ (K+1)(nnzPu + 2 nnzA) + 2 nnzA + (6K+8) n + (2K+12) m ]      per ADMM iteration, K = KKT solves / iteration
+        bytes_check   = 8 [ nnzPu + 2 nnzA + 4n + 4m ]                                    per residual check
+    (K = 1 for the direct LDL' kernel: one application of the factor per iteration.)  Returns (contract bytes, counts,
+    direct-model bytes or None).  The direct model (DESIGN.md 5.3, round 1's figure) counts what the block LDL' reads --
+    dense factor blocks instead of PCG operator applications, plus the set-up -- and is kept for comparison only."""
     n, m, nnz_a = dims["n"], dims["m"], dims["nnz_a"]
     iters = stats[:, ocp.STAT["admm_iters"]].sum()
-    pcg = stats[:, ocp.STAT["pcg_iters"]].sum()
+    solves = stats[:, ocp.STAT["pcg_iters"]].sum()
     checks = stats[:, ocp.STAT["checks"]].sum()
+    qps = stats[:, ocp.STAT["sqp_steps"]].sum()
     mat = nnz_pu + 2 * nnz_a
+    contract = 8.0 * ((solves + iters) * mat + iters * (2 * nnz_a + 8 * n + 12 * m) + solves * (6 * n + 2 * m)) \
+        + 8.0 * checks * (mat + 4 * n + 4 * m)
+    counts = dict(admm_iters=float(iters), kkt_solves=float(solves), checks=float(checks), qps=float(qps),
+                  K=float(solves / max(iters, 1.0)))
+    model = None
     if direct is not None:
         np_, bs, nb = direct["np"], direct["bs"], direct["nb"]
         fac = nb * bs * bs + 2 * (nb - 1) * bs * bs + 2 * np_ * nb * bs + np_ * np_
         per_iter = 8.0 * (2 * nnz_a + fac + 10 * n + 9 * m)
-        qps = stats[:, ocp.STAT["sqp_steps"]].sum()
         setup = 8.0 * ((nnz_a + nnz_pu + n + 2 * m) + 10 * 3 * (2 * nnz_pu + nnz_a) + 4 * fac)
-        check = 8.0 * checks * (mat + 4 * n + 4 * m)
-        return iters * per_iter + qps * setup + check, dict(admm_iters=float(iters), kkt_solves=float(pcg),
-                                                            checks=float(checks), qps=float(qps))
-    admm = 8.0 * ((pcg + iters) * mat + iters * (2 * nnz_a + 8 * n + 12 * m) + pcg * (6 * n + 2 * m))
-    check = 8.0 * checks * (mat + 4 * n + 4 * m)
-    return admm + check, dict(admm_iters=float(iters), pcg_iters=float(pcg), checks=float(checks))
+        model = iters * per_iter + qps * setup + 8.0 * checks * (mat + 4 * n + 4 * m)
+    return contract, counts, model
+
+
+def secondary_pass(ocp, torch, dist, world, rank, local, dev):
+    """BASELINE.json configs[3] (16 384 centroidal instances) and configs[4] (65 536 cart-pole instances) at their stated
+    TOTAL sizes, split evenly over the ranks (strong scaling), one warm-up and one timed batched solve each, device-timed
+    with the gather of solutions and statistics inside; max over ranks."""
+    from optimal_control_problem_b200.sharding import gather_shards
+    out = []
+    for name, total, cfg in (("centroidal", 16384, "BASELINE.json configs[3]"), ("cartpole", 65536, "BASELINE.json configs[4]")):
+        Bk = total // world
+        prob = ocp.Problem(name, alpha=ALPHA, step_num=STEP_NUM)
+        sol = ocp.Solver.create(prob.n, prob.m, prob.h_colptr, prob.h_rowidx, prob.a_colptr, prob.a_rowidx,
+                                settings=prob.get_settings(), np_=prob.np_, nf=prob.nf, horizon=prob.horizon,
+                                model_library=prob.model_library, device=local)
+        frames_h, refs_h = prob.sample_inputs(Bk, SEED + 7 + 1000 * rank)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        d_frames, d_p, d_lbx, d_ubx, d_lbg, d_ubg = t(frames_h), t(refs_h), t(prob.lbx), t(prob.ubx), t(prob.lbg), t(prob.ubg)
+        d_x0 = t(np.tile(frames_h, (1, prob.horizon)))
+        d_x = torch.zeros(Bk, prob.N, dtype=torch.float64, device=dev)
+        d_f = torch.zeros(Bk, dtype=torch.float64, device=dev)
+        d_st = torch.zeros(Bk, ocp.NSTATS, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream()
+        ms = 0.0
+        for it in range(2):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            d_x.copy_(d_x0)
+            sol.solve_batch_device(Bk, d_frames.data_ptr(), d_p.data_ptr(), d_lbx.data_ptr(), d_ubx.data_ptr(), d_lbg.data_ptr(),
+                                   d_ubg.data_ptr(), d_x.data_ptr(), d_f.data_ptr(), d_st.data_ptr(), stream.cuda_stream)
+            if world > 1:
+                gather_shards(d_x, world * Bk); gather_shards(d_st, world * Bk)
+            e1.record(stream)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        st = d_st.cpu().numpy()
+        out.append({"workload": f"{WORKLOADS[name][0]} ({cfg})", "total_instances": world * Bk, "instances_per_gpu": Bk,
+                    "scaling": "strong", "value": world * Bk / (float(tm.item()) * 1e-3), "unit": UNIT,
+                    "ms_per_step": float(tm.item()), "steps": 1, "warmup": 1,
+                    "admm_iters_per_solve": float(st[:, ocp.STAT["admm_iters"]].mean()),
+                    "solved_fraction_rank0": float((st[:, ocp.STAT["qp_status"]] == ocp.QP_SOLVED).mean()),
+                    "plan": sol.launch_plan()["wide"]})
+        sol.close()
+        del d_x, d_x0, d_st, d_f
+        torch.cuda.empty_cache()
+    return out
 
 
 def b200_arm(args):
@@ -322,23 +383,25 @@ def b200_arm(args):
     stats_h = d_stats.cpu().numpy()
     solved = int((stats_h[:, ocp.STAT["qp_status"]] == ocp.QP_SOLVED).sum())
     dd = sol.device_dims()
-    direct = None
-    if dd["resident"] & 2:
-        G = max(g for g in range(1, prob.horizon + 1) if prob.horizon % g == 0 and (g * prob.nf <= 20 or g == 1))
-        direct = dict(np=prob.np_, bs=G * prob.nf, nb=prob.horizon // G)
-    bytes_per_solve_call, counts = algorithmic_bytes(dims, nnz_pu, stats_h, ocp, direct)
+    plan = sol.launch_plan()
+    direct = dict(np=plan["tri_np"], bs=plan["tri_bs"], nb=plan["tri_nb"]) if plan["tri_ok"] else None   # from the handle
+    bytes_per_solve_call, counts, model_bytes = algorithmic_bytes(dims, nnz_pu, stats_h, ocp, direct)
     admm_ms_per_launch = prof["admm"]["ms"] / max(1, prof["admm"]["launches"])
     bytes_per_launch = bytes_per_solve_call / STEP_NUM
     achieved = bytes_per_launch / (admm_ms_per_launch * 1e-3) / 1e9 if admm_ms_per_launch > 0 else 0.0
+    model_achieved = (model_bytes / STEP_NUM) / (admm_ms_per_launch * 1e-3) / 1e9 if model_bytes and admm_ms_per_launch > 0 else None
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    traffic = None
+    # DRAM traffic and issue / occupancy counters of the same kernel from the committed ncu capture (profiles/)
+    traffic, counters = None, None
     tpath = ROOT / "profiles" / "admm_traffic.json"
-    if tpath.exists():
-        traffic = json.loads(tpath.read_text()).get("dram_bytes_per_launch")
+    if tpath.exists() and PROBLEM == "quadrotor":
+        tj = json.loads(tpath.read_text())
+        traffic = tj.get("dram_bytes_per_launch")
+        counters = tj.get("counters")
 
     # ---- e2e: pinned host buffers through ocp_b200_solve_batch -----------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -394,6 +457,13 @@ def b200_arm(args):
                "single_thread_ms_per_solve": 1e3 * t1, "single_thread_p50_ms": p50_1t["p50_ms"],
                "single_thread_p50_solves": p50_1t["solves"], "value_without_resetup": sample / tr}
 
+    # ---- BASELINE.json configs[3] / [4] at their stated total sizes (strong scaling over the ranks) ------------
+    secondary = None
+    if PROBLEM == "quadrotor" and (args.secondary == "on" or (args.secondary == "auto" and world >= 2)):
+        del flush
+        torch.cuda.empty_cache()
+        secondary = secondary_pass(ocp, torch, dist, world, rank, local, dev)
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -404,7 +474,16 @@ def b200_arm(args):
                         "max_abs_diff_vs_device_path": e2e_match},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "admm_solve_kernel", "peak_source": peak_src,
+                             "traffic": traffic,
+                             "kernel": {4: "admm_compact_kernel", -1: "admm_solve_kernel (PCG)"}.get(plan["wide"]["place"], "admm_direct_kernel"),
+                             "peak_source": peak_src,
+                             "formula": "SURVEY.md 8(d): iters*bytes_admm(K) + checks*bytes_check, K = kkt_solves/admm_iters from the stats buffer",
+                             "limiter": "dependent-instruction latency: per-instance state lives in shared memory and an L2-resident slab, "
+                                        "`achieved` is an effective (algorithmic) rate, not DRAM utilisation",
+                             "achieved_dram": (traffic / (admm_ms_per_launch * 1e-3) / 1e9) if traffic and admm_ms_per_launch > 0 else None,
+                             "frac_dram": (traffic / (admm_ms_per_launch * 1e-3) / 1e9 / peak) if traffic and admm_ms_per_launch > 0 else None,
+                             "frac_direct_model": (model_achieved / peak) if model_achieved else None,
+                             "counters": counters,
                              "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms_per_launch": admm_ms_per_launch,
                              "kernel_share_of_step": prof["admm"]["ms"] / max(total_ms, 1e-9),
                              "assemble_ms_per_launch": prof["assemble"]["ms"] / max(1, prof["assemble"]["launches"]),
@@ -413,7 +492,11 @@ def b200_arm(args):
                 "clocks": clocks,
                 "latency_p50_ms": float(np.median(lat)) if lat else None,
                 "solved_fraction": solved / B,
-                "device": torch.cuda.get_device_name(local), "kernel_plan": dict(dd, linsys="block-tridiagonal LDL' (direct)" if direct else "PCG")}
+                "device": torch.cuda.get_device_name(local),
+                "kernel_plan": dict(dd, linsys="block-tridiagonal LDL' (direct)" if direct else "PCG", wide=plan["wide"], deep=plan["deep"],
+                                    tri=direct)}
+        if secondary is not None:
+            line["secondary"] = secondary
         emit(line)
     if world > 1:
         dist.destroy_process_group()

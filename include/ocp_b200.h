@@ -232,6 +232,30 @@ int ocp_b200_get_profile(ocp_b200_solver* s, double* ms, long long* count, int r
 int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int* nnz_a,
                       int* smem_bytes, int* resident);
 
+/* ---- several GPUs of one node from ONE process ---------------------------------------------
+ * The reference is single-instance, single-device; a C++ user of OptimalControlProblem reaches more than one GPU
+ * through these entry points (OptimalControlProblem::computeOptimalTrajectoryBatch uses them when more than one
+ * device is configured).  Instances are independent, so the batch is cut into contiguous blocks of ceil(B / ndev)
+ * instances, one block per device in the order of `devices`; every device has its own handle, stream and slabs and
+ * is driven by its own host thread; there is no traffic between the devices -- the "gather" is each device's
+ * device-to-host copy landing in its slice of the caller's arrays.  (Device-resident multi-GPU batches, one process
+ * per GPU with an NCCL all-gather, are what optimal_control_problem_b200/sharding.py and bench.py do.) */
+typedef struct ocp_b200_multi ocp_b200_multi;
+
+/* one handle per entry of devices[0..ndev) (a device may be listed more than once); desc->device is ignored */
+int ocp_b200_create_multi(const ocp_b200_problem_desc* desc, const ocp_b200_settings* settings, const int* devices,
+                          int ndev, ocp_b200_multi** out);
+int ocp_b200_destroy_multi(ocp_b200_multi* m);
+int ocp_b200_multi_update_settings(ocp_b200_multi* m, const ocp_b200_settings* settings);
+/* offsets[0..ndev]: instance range [offsets[k], offsets[k+1]) goes to device k.  Pure arithmetic, needs no GPU. */
+int ocp_b200_multi_partition(int B, int ndev, int* offsets);
+int ocp_b200_multi_device_count(const ocp_b200_multi* m);
+ocp_b200_solver* ocp_b200_multi_handle(ocp_b200_multi* m, int k);   /* borrowed: settings queries, profiling */
+/* same arguments and results as ocp_b200_solve_batch; bit-identical to it for every instance */
+int ocp_b200_solve_batch_multi(ocp_b200_multi* m, int B, const double* frames, const double* p, const double* lbx,
+                               const double* ubx, const double* lbg, const double* ubg, double* x_inout,
+                               double* f_out, double* stats);
+
 /* launch plan and linear-system structure of a handle (diagnostics, roofline accounting): fills up to
  * `count` ints of v in the order of the OCP_B200_PLAN_* slots */
 #define OCP_B200_PLAN_WIDE_PLACE      0   /* throughput plan: placement id (0 mixed, 1 all shared, 2 multi-CTA, 3 big) */

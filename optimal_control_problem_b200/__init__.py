@@ -118,6 +118,14 @@ def cuda_lib() -> C.CDLL:
         lib.ocp_b200_admm_trace.argtypes = [vptr] + [dptr] * 5 + [C.c_int, dptr, C.POINTER(C.c_int), dptr, dptr]
         lib.ocp_b200_get_dims.argtypes = [vptr] + [C.POINTER(C.c_int)] * 6
         lib.ocp_b200_get_plan.argtypes = [vptr, C.POINTER(C.c_int), C.c_int]
+        lib.ocp_b200_create_multi.argtypes = [C.POINTER(ProblemDesc), C.POINTER(Settings), C.POINTER(C.c_int), C.c_int, C.POINTER(vptr)]
+        lib.ocp_b200_destroy_multi.argtypes = [vptr]
+        lib.ocp_b200_multi_update_settings.argtypes = [vptr, C.POINTER(Settings)]
+        lib.ocp_b200_multi_partition.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+        lib.ocp_b200_multi_device_count.argtypes = [vptr]
+        lib.ocp_b200_multi_handle.argtypes = [vptr, C.c_int]
+        lib.ocp_b200_multi_handle.restype = vptr
+        lib.ocp_b200_solve_batch_multi.argtypes = [vptr, C.c_int] + [dptr] * 9
         lib.ocp_b200_set_profiling.argtypes = [vptr, C.c_int]
         lib.ocp_b200_get_profile.argtypes = [vptr, dptr, C.POINTER(C.c_longlong), C.c_int]
         lib.ocp_b200_get_phase_cycles.argtypes = [vptr, C.POINTER(C.c_longlong)]
@@ -153,6 +161,9 @@ def host_lib() -> C.CDLL:
         lib.ocp_host_compute_optimal_trajectory_batch.argtypes = [vptr, C.c_int, dptr, dptr, dptr, dptr, dptr]
         lib.ocp_host_problem_reset.argtypes = [vptr]
         lib.ocp_host_problem_shift_batch.argtypes = [vptr]
+        lib.ocp_host_problem_set_devices.argtypes = [vptr, C.POINTER(C.c_int), C.c_int]
+        lib.ocp_host_problem_generate_c.argtypes = [vptr, C.c_char_p]
+        lib.ocp_host_compile_casadi_c.argtypes = [C.c_char_p] * 4 + [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
         pv = C.POINTER(vptr)
         lib.ocp_host_sx_sym.argtypes = [C.c_char_p, C.c_int, pv]
         lib.ocp_host_sx_const.argtypes = [dptr, C.c_int, pv]
@@ -200,6 +211,63 @@ def _check(rc: int) -> None:
 def _hcheck(rc: int) -> None:
     if rc != 0:
         raise RuntimeError(host_lib().ocp_host_last_error().decode())
+
+
+def multi_partition(B: int, ndev: int) -> np.ndarray:
+    """``ocp_b200_multi_partition``: instance offsets of the contiguous block partition over ``ndev`` devices."""
+    off = np.zeros(ndev + 1, np.int32)
+    _check(cuda_lib().ocp_b200_multi_partition(int(B), int(ndev), _ip(off)))
+    return off
+
+
+class MultiSolver:
+    """``ocp_b200_create_multi`` / ``ocp_b200_solve_batch_multi``: one process, several GPUs (or several handles on one)."""
+
+    def __init__(self, problem: "Problem", devices, settings: Settings | None = None):
+        hc, hr = np.ascontiguousarray(problem.h_colptr, np.int32), np.ascontiguousarray(problem.h_rowidx, np.int32)
+        ac, ar = np.ascontiguousarray(problem.a_colptr, np.int32), np.ascontiguousarray(problem.a_rowidx, np.int32)
+        d = ProblemDesc()
+        d.np, d.nf, d.horizon, d.ng = problem.np_, problem.nf, problem.horizon, problem.ng
+        d.nnz_h, d.h_colptr, d.h_rowidx = hr.size, _ip(hc), _ip(hr)
+        d.nnz_a, d.a_colptr, d.a_rowidx = ar.size, _ip(ac), _ip(ar)
+        d.model_library = problem.model_library.encode()
+        dev = np.ascontiguousarray(list(devices), np.int32)
+        s = settings if settings is not None else problem.get_settings()
+        out = C.c_void_p()
+        _check(cuda_lib().ocp_b200_create_multi(C.byref(d), C.byref(s), _ip(dev), int(dev.size), C.byref(out)))
+        self._h, self.problem, self.devices = out, problem, dev.tolist()
+
+    def update_settings(self, s: Settings) -> None:
+        _check(cuda_lib().ocp_b200_multi_update_settings(self._h, C.byref(s)))
+
+    def solve_batch(self, frames, p, x_inout, f_out=None, stats=None):
+        pr = self.problem
+        B = x_inout.size // pr.N
+        frames = _f64(frames, (B, pr.nf)) if frames is not None else None
+        _check(cuda_lib().ocp_b200_solve_batch_multi(self._h, B, _dp(frames), _dp(_f64(p, (B, pr.np_))), _dp(pr.lbx), _dp(pr.ubx),
+                                                    _dp(pr.lbg), _dp(pr.ubg), _dp(x_inout), _dp(f_out), _dp(stats)))
+
+    def close(self) -> None:
+        if self._h:
+            cuda_lib().ocp_b200_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compile_casadi_c(c_file: str, nf: int, horizon: int, name: str = "model", local_system_fn: str = "localSystemFunction",
+                     objective_fn: str = "objective", code_dir: str | None = None) -> str:
+    """A CasADi-generated C file (``Function::generate`` layout) -> stage library for ``Solver.create(model_library=...)``
+    (host/src/CasadiCInterop.cpp).  Needs nvcc and a C compiler, no GPU."""
+    code_dir = code_dir or str(_PKG / "share" / "code_gen")
+    out = C.create_string_buffer(4096)
+    _hcheck(host_lib().ocp_host_compile_casadi_c(str(c_file).encode(), local_system_fn.encode(), objective_fn.encode(), name.encode(),
+                                                 int(nf), int(horizon), code_dir.encode(), out, 4096))
+    return out.value.decode()
 
 
 def default_settings() -> Settings:
@@ -448,6 +516,17 @@ class Problem:
                                                                      _dp(_f64(references, (B, self.np_))), _dp(x),
                                                                      _dp(f), _dp(st)))
         return x, f, st
+
+    def generate_c(self, path: str) -> str:
+        """Writes localSystemFunction + objective as one C file in the layout of CasADi's code generator."""
+        _hcheck(host_lib().ocp_host_problem_generate_c(self._h, str(path).encode()))
+        return str(path)
+
+    def set_devices(self, devices) -> None:
+        """``SQPOptimizationSolver::setDevices``: the GPUs ``compute_optimal_trajectory_batch`` spreads a batch over
+        (contiguous blocks, ``ocp_b200_create_multi``); a device may be listed twice."""
+        d = np.ascontiguousarray(list(devices), dtype=np.int32)
+        _hcheck(host_lib().ocp_host_problem_set_devices(self._h, _ip(d), int(d.size)))
 
     def reset(self) -> None:
         _hcheck(host_lib().ocp_host_problem_reset(self._h))

@@ -38,6 +38,7 @@ HOST_SOURCES = [
     "host/src/AutoDifferentiator.cpp",
     "host/src/SQPOptimizationSolver.cpp",
     "host/src/StageCodegen.cpp",
+    "host/src/CasadiCInterop.cpp",
     "host/src/CuCaQP.cpp",
     "host/src/host_capi.cpp",
     "problems/problems.cpp",
@@ -122,7 +123,7 @@ def build_host(force: bool = False) -> Path:
     objs = compile_objects(HOST_SOURCES, HOST_FLAGS, OBJ)
     if force or _stale(out, objs + [cuda]):
         _run([CXX, "-shared", "-o", str(out), *map(str, objs), "-L" + str(LIB), "-locp_b200", "-Wl,-rpath,$ORIGIN",
-              "-pthread"])
+              "-pthread", "-ldl"])
     return out
 
 

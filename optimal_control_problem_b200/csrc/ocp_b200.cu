@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "admm_pcg_kernel.cuh"
@@ -1029,6 +1030,92 @@ int ocp_b200_get_dims(const ocp_b200_solver* s, int* n, int* m, int* nnz_h, int*
   if (nnz_a) *nnz_a = s->nnz_a;
   if (smem_bytes) *smem_bytes = s->smem_bytes;
   if (resident) *resident = s->resident | (s->use_direct << 1) | (s->place << 2);
+  return OCP_B200_OK;
+}
+
+// ---- several devices from one process ------------------------------------------------------------------------
+struct ocp_b200_multi {
+  std::vector<ocp_b200_solver*> handles;
+  std::vector<int> devices;
+  int np = 0, nf = 0, N = 0;
+};
+
+int ocp_b200_multi_partition(int B, int ndev, int* offsets) {
+  if (B < 0 || ndev <= 0 || !offsets) return fail(OCP_B200_ERR_INVALID, "bad arguments to multi_partition");
+  const int per = (B + ndev - 1) / ndev;   // contiguous blocks of ceil(B / ndev), the tail devices may get less / nothing
+  for (int k = 0; k <= ndev; ++k) offsets[k] = std::min(B, k * per);
+  return OCP_B200_OK;
+}
+
+int ocp_b200_create_multi(const ocp_b200_problem_desc* desc, const ocp_b200_settings* settings, const int* devices,
+                          int ndev, ocp_b200_multi** out) {
+  if (!desc || !out || !devices || ndev <= 0) return fail(OCP_B200_ERR_INVALID, "bad arguments to create_multi");
+  *out = nullptr;
+  ocp_b200_multi* m = new (std::nothrow) ocp_b200_multi();
+  if (!m) return fail(OCP_B200_ERR_INVALID, "out of host memory");
+  for (int k = 0; k < ndev; ++k) {
+    ocp_b200_problem_desc d = *desc;
+    d.device = devices[k];
+    ocp_b200_solver* h = nullptr;
+    const int rc = ocp_b200_create(&d, settings, &h);
+    if (rc != OCP_B200_OK) {
+      const std::string keep = g_error;
+      ocp_b200_destroy_multi(m);
+      return fail(rc, "device " + std::to_string(devices[k]) + ": " + keep);
+    }
+    m->handles.push_back(h);
+    m->devices.push_back(devices[k]);
+  }
+  m->np = desc->np; m->nf = desc->nf; m->N = desc->nf * desc->horizon;
+  *out = m;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_destroy_multi(ocp_b200_multi* m) {
+  if (!m) return OCP_B200_OK;
+  for (ocp_b200_solver* h : m->handles) ocp_b200_destroy(h);
+  delete m;
+  return OCP_B200_OK;
+}
+
+int ocp_b200_multi_update_settings(ocp_b200_multi* m, const ocp_b200_settings* settings) {
+  if (!m) return fail(OCP_B200_ERR_INVALID, "multi handle is NULL");
+  for (ocp_b200_solver* h : m->handles) RC_TRY(ocp_b200_update_settings(h, settings));
+  return OCP_B200_OK;
+}
+
+int ocp_b200_multi_device_count(const ocp_b200_multi* m) { return m ? static_cast<int>(m->handles.size()) : 0; }
+ocp_b200_solver* ocp_b200_multi_handle(ocp_b200_multi* m, int k) {
+  return (m && k >= 0 && k < static_cast<int>(m->handles.size())) ? m->handles[k] : nullptr;
+}
+
+int ocp_b200_solve_batch_multi(ocp_b200_multi* m, int B, const double* frames, const double* p, const double* lbx,
+                               const double* ubx, const double* lbg, const double* ubg, double* x_inout,
+                               double* f_out, double* stats) {
+  if (!m || m->handles.empty()) return fail(OCP_B200_ERR_INVALID, "multi handle is NULL");
+  if (B < 0) return fail(OCP_B200_ERR_INVALID, "bad arguments to solve_batch_multi");
+  if (B == 0) return OCP_B200_OK;
+  const int ndev = static_cast<int>(m->handles.size());
+  std::vector<int> off(ndev + 1);
+  RC_TRY(ocp_b200_multi_partition(B, ndev, off.data()));
+  std::vector<int> rc(ndev, OCP_B200_OK);
+  std::vector<std::string> err(ndev);
+  auto work = [&](int k) {
+    const int b0 = off[k], nb = off[k + 1] - off[k];
+    if (nb <= 0) return;
+    rc[k] = ocp_b200_solve_batch(m->handles[k], nb, frames ? frames + size_t(b0) * m->nf : nullptr,
+                                 p ? p + size_t(b0) * m->np : nullptr, lbx, ubx, lbg, ubg,
+                                 x_inout ? x_inout + size_t(b0) * m->N : nullptr, f_out ? f_out + b0 : nullptr,
+                                 stats ? stats + size_t(b0) * OCP_B200_NSTATS : nullptr);
+    if (rc[k] != OCP_B200_OK) err[k] = g_error;   // g_error is per thread
+  };
+  // one host thread per device: every ocp_b200_solve_batch uploads, launches, downloads and waits on its own stream
+  std::vector<std::thread> threads;
+  for (int k = 1; k < ndev; ++k) threads.emplace_back(work, k);
+  work(0);
+  for (std::thread& t : threads) t.join();
+  for (int k = 0; k < ndev; ++k)
+    if (rc[k] != OCP_B200_OK) return fail(rc[k], "device " + std::to_string(m->devices[k]) + ": " + err[k]);
   return OCP_B200_OK;
 }
 

@@ -403,10 +403,27 @@ class Function {
   // text serialisation of the tape (stand-in for casadi::Function::save,
   // src/OptimalControlProblem.cpp:412)
   void save(const std::string& filename) const;
+  // C source in the layout of casadi::Function::generate / casadi::CodeGenerator: casadi_real / casadi_int,
+  // `int name(const casadi_real** arg, casadi_real** res, casadi_int* iw, casadi_real* w, int mem)`, compact CCS
+  // `name_sparsity_in/out`, `name_n_in/out`, `name_name_in/out`, `name_work`.  Intermediates live in w[] (what CasADi
+  // does for MX functions; its SX functions use locals -- both honour the same signature).
+  void generate(const std::string& filename) const;
+  void generate_body(std::ostream& os, int index) const;   // one function of a multi-function file (CodeGenerator)
 
  private:
   struct Data;
   std::shared_ptr<const Data> d_;
+};
+
+// casadi::CodeGenerator subset: several functions in one C file
+class CodeGenerator {
+ public:
+  explicit CodeGenerator(const std::string& name) : name_(name) {}
+  void add(const Function& f) { fs_.push_back(f); }
+  std::string generate(const std::string& prefix = "") const;   // writes <prefix><name>, returns the path
+ private:
+  std::string name_;
+  std::vector<Function> fs_;
 };
 
 // ---------------------------------------------------------------------------

@@ -38,6 +38,13 @@ ModelSource generate(const ModelSpec& spec);
 std::string compile(const ModelSource& src, const std::string& name, const std::string& code_dir,
                     bool verbose);
 
+// A CasADi-generated C file (Function::generate / CodeGenerator layout) as the stage library: `local_system_fn`
+// maps (p, x, l, u) -> (H, grad f, J, l - c, u - c), `objective_fn` maps (p, x) -> f; nf / horizon give the stage
+// layout of x.  Compiles <code_dir>/<name>_casadi_<hash>.so (host build for the sparsity queries, then nvcc with the
+// C functions as __device__ code, one thread per instance) and returns its path.  See CasadiCInterop.cpp.
+std::string compile_casadi_c(const std::string& c_file, const std::string& local_system_fn, const std::string& objective_fn,
+                             const std::string& name, int nf, int horizon, const std::string& code_dir, bool verbose);
+
 // directory holding ocp_b200.h / ocp_b200_model.h ($OCP_B200_INCLUDE_DIR or relative to this file)
 std::string include_dir();
 

@@ -40,6 +40,12 @@ class SQPOptimizationSolver {
   // local system at the current iterate via the GPU assembly kernel (parity hook)
   casadi::DMVector getLocalSystemGPU(const casadi::DMDict& arg);
 
+  // Batched solves on several GPUs of the node (include/ocp_b200.h: ocp_b200_create_multi): the batch is cut into
+  // contiguous blocks, one per listed device.  An empty list / one entry = the single device of `options["device"]`.
+  // The environment variable OCP_B200_DEVICES ("0,1,2,3") sets the list for programs that cannot be changed.
+  void setDevices(const std::vector<int>& devices);
+  const std::vector<int>& devices() const { return devices_; }
+
   void ensureDevice();  // creates the device solver; throws when no CUDA device is usable
   ocp_b200_solver* handle() { ensureDevice(); return handle_; }
   ocp_b200_settings& settings() { return settings_; }
@@ -69,5 +75,7 @@ class SQPOptimizationSolver {
   std::vector<int> hColptr_, hRowidx_, aColptr_, aRowidx_;
   std::string modelLibrary_;
   ocp_b200_solver* handle_{nullptr};
+  ocp_b200_multi* multi_{nullptr};
+  std::vector<int> devices_;
   ocp_b200_settings settings_;
 };

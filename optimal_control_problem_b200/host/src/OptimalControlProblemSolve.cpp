@@ -32,6 +32,12 @@ void OptimalControlProblem::genSolver() {
       // the reference serialises localSystemFunction here (:403-425)
       const std::string target = codeDir + "/localSystemFunction.casadi";
       OSQPSolverPtr_->getSXLocalSystemFunction().save(target);
+      // ... and, in the layout of CasADi's C code generator, as a file that CasadiCInterop.cpp (or any consumer of
+      // CasADi-generated C) can compile: localSystemFunction + objective
+      casadi::CodeGenerator cg(codeDir + "/localSystemFunction.c");
+      cg.add(OSQPSolverPtr_->getSXLocalSystemFunction());
+      cg.add(OSQPSolverPtr_->getObjectiveFunction());
+      cg.generate();
       if (solverSettings.verbose) std::cout << "LocalSystemFunction saved to: " << target << std::endl;
     }
     if (solverSettings.verbose) {

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <iomanip>
 #include <iostream>
+#include <sstream>
 
 #include "optimal_control_problem/codegen/StageCodegen.h"
 
@@ -93,6 +94,13 @@ SQPOptimizationSolver::SQPOptimizationSolver(SXDict& nlp, Dict& options) : verbo
   aColptr_ = toInt(linearized[0].sparsity().get_colind()); aRowidx_ = toInt(linearized[0].sparsity().get_row());
   nf_ = spec.nf; horizon_ = spec.horizon;
   device_ = options.count("device") ? static_cast<int>(options.at("device").as_int()) : 0;
+  if (const char* e = std::getenv("OCP_B200_DEVICES")) {   // "0,1,2,3": devices of the batched entry point
+    std::vector<int> list;
+    std::stringstream ss(e);
+    for (std::string tok; std::getline(ss, tok, ',');)
+      if (!tok.empty()) list.push_back(std::atoi(tok.c_str()));
+    devices_ = list;
+  }
   // The device handle is created on first use (ensureDevice) so that the symbolic set-up and
   // the nvcc build can run on a machine without a GPU; every solve entry point needs the GPU.
 
@@ -100,7 +108,14 @@ SQPOptimizationSolver::SQPOptimizationSolver(SXDict& nlp, Dict& options) : verbo
 }
 
 SQPOptimizationSolver::~SQPOptimizationSolver() {
+  if (multi_) ocp_b200_destroy_multi(multi_);
   if (handle_) ocp_b200_destroy(handle_);
+}
+
+void SQPOptimizationSolver::setDevices(const std::vector<int>& devices) {
+  if (devices == devices_) return;
+  if (multi_) { ocp_b200_destroy_multi(multi_); multi_ = nullptr; }
+  devices_ = devices;
 }
 
 void SQPOptimizationSolver::ensureDevice() {
@@ -191,6 +206,22 @@ void SQPOptimizationSolver::getOptimalSolutionBatch(int B, const std::vector<dou
   if (stats) stats->assign(static_cast<size_t>(B) * OCP_B200_NSTATS, 0.0);
   settings_.sqp_step_num = stepNum_;
   settings_.sqp_alpha = alpha_;
+  if (devices_.size() > 1) {   // several GPUs: contiguous blocks of the batch, one host thread per device
+    if (!multi_) {
+      ocp_b200_problem_desc desc{};
+      desc.np = np_; desc.nf = nf_; desc.horizon = horizon_; desc.ng = ng_;
+      desc.nnz_h = static_cast<int>(hRowidx_.size()); desc.h_colptr = hColptr_.data(); desc.h_rowidx = hRowidx_.data();
+      desc.nnz_a = static_cast<int>(aRowidx_.size()); desc.a_colptr = aColptr_.data(); desc.a_rowidx = aRowidx_.data();
+      desc.model_library = modelLibrary_.c_str();
+      check(ocp_b200_create_multi(&desc, &settings_, devices_.data(), static_cast<int>(devices_.size()), &multi_),
+            "ocp_b200_create_multi");
+    }
+    check(ocp_b200_multi_update_settings(multi_, &settings_), "ocp_b200_multi_update_settings");
+    check(ocp_b200_solve_batch_multi(multi_, B, frames.empty() ? nullptr : frames.data(), p.data(), lx.data(), ux.data(),
+                                     lg.data(), ug.data(), x_inout.data(), f_out.data(), stats ? stats->data() : nullptr),
+          "ocp_b200_solve_batch_multi");
+    return;
+  }
   applySettings();
   check(ocp_b200_solve_batch(handle_, B, frames.empty() ? nullptr : frames.data(), p.data(), lx.data(),
                              ux.data(), lg.data(), ug.data(), x_inout.data(), f_out.data(),

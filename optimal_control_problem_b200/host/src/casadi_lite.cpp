@@ -1089,4 +1089,145 @@ void Function::save(const std::string& filename) const {
   for (const Data::Instr& t : d.tape) f << op_name(t.op) << " " << t.res << " " << t.a << " " << t.b << "\n";
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// C code generation in CasADi's format (casadi/core/code_generator.cpp, function_internal.cpp of upstream
+// define the layout; written from the published structure of generated files, not from their sources)
+// ---------------------------------------------------------------------------------------------
+namespace {
+const char* kCHeader =
+    "/* This file was automatically generated by casadi-lite (optimal_control_problem_b200) in the format of\n"
+    "   CasADi's C code generator (Function::generate): same preamble, signatures and sparsity encoding. */\n"
+    "#ifdef __cplusplus\nextern \"C\" {\n#endif\n\n"
+    "/* How to prefix internal symbols */\n#ifdef CASADI_CODEGEN_PREFIX\n"
+    "  #define CASADI_NAMESPACE_CONCAT(NS, ID) _CASADI_NAMESPACE_CONCAT(NS, ID)\n"
+    "  #define _CASADI_NAMESPACE_CONCAT(NS, ID) NS ## ID\n"
+    "  #define CASADI_PREFIX(ID) CASADI_NAMESPACE_CONCAT(CODEGEN_PREFIX, ID)\n#else\n"
+    "  #define CASADI_PREFIX(ID) %s_ ## ID\n#endif\n\n#include <math.h>\n\n"
+    "#ifndef casadi_real\n#define casadi_real double\n#endif\n\n#ifndef casadi_int\n#define casadi_int long long int\n#endif\n\n"
+    "/* Add prefix to internal symbols */\n#define casadi_f0 CASADI_PREFIX(f0)\n#define casadi_sq CASADI_PREFIX(sq)\n"
+    "#define casadi_sign CASADI_PREFIX(sign)\n#define casadi_fmin CASADI_PREFIX(fmin)\n#define casadi_fmax CASADI_PREFIX(fmax)\n\n"
+    "/* Symbol visibility in DLLs */\n#ifndef CASADI_SYMBOL_EXPORT\n"
+    "  #if defined(_WIN32) || defined(__WIN32__) || defined(__CYGWIN__)\n    #if defined(STATIC_LINKED)\n"
+    "      #define CASADI_SYMBOL_EXPORT\n    #else\n      #define CASADI_SYMBOL_EXPORT __declspec(dllexport)\n    #endif\n"
+    "  #elif defined(__GNUC__) && defined(GCC_HASCLASSVISIBILITY)\n"
+    "    #define CASADI_SYMBOL_EXPORT __attribute__ ((visibility (\"default\")))\n  #else\n    #define CASADI_SYMBOL_EXPORT\n  #endif\n#endif\n\n"
+    "static casadi_real casadi_sq(casadi_real x) { return x*x;}\n\n"
+    "static casadi_real casadi_sign(casadi_real x) { return x<0 ? -1 : x>0 ? 1 : x;}\n\n"
+    "static casadi_real casadi_fmin(casadi_real x, casadi_real y) { return x<y ? x : y;}\n\n"
+    "static casadi_real casadi_fmax(casadi_real x, casadi_real y) { return x>y ? x : y;}\n\n";
+
+std::string c_expr(int op, const std::string& a, const std::string& b) {
+  switch (op) {
+    case OP_ADD: return "(" + a + "+" + b + ")";
+    case OP_SUB: return "(" + a + "-" + b + ")";
+    case OP_MUL: return "(" + a + "*" + b + ")";
+    case OP_DIV: return "(" + a + "/" + b + ")";
+    case OP_POW: return "pow(" + a + "," + b + ")";
+    case OP_ATAN2: return "atan2(" + a + "," + b + ")";
+    case OP_FMIN: return "casadi_fmin(" + a + "," + b + ")";
+    case OP_FMAX: return "casadi_fmax(" + a + "," + b + ")";
+    case OP_LT: return "(" + a + "<" + b + ")";
+    case OP_NEG: return "(-" + a + ")";
+    case OP_SQ: return "casadi_sq(" + a + ")";
+    case OP_SIGN: return "casadi_sign(" + a + ")";
+    default: return std::string(op_name(op)) + "(" + a + ")";   // sqrt sin cos tan asin acos atan exp log fabs tanh sinh cosh
+  }
+}
+}  // namespace
+
+void Function::generate_body(std::ostream& os, int index) const {
+  casadi_assert(d_, "generate of a null Function");
+  const Data& d = *d_;
+  const std::string& nm = d.name;
+  os << std::setprecision(17);
+  // compact CCS: {nrow, ncol, colind[0..ncol], row[0..nnz)}; dense patterns as {nrow, ncol, 1}
+  auto sp_array = [&](const Sparsity& sp, const std::string& id) {
+    std::vector<casadi_int> v{sp.size1(), sp.size2()};
+    if (sp.is_dense() && sp.numel() > 0) {
+      v.push_back(1);
+    } else {
+      for (casadi_int c : sp.get_colind()) v.push_back(c);
+      for (casadi_int r : sp.get_row()) v.push_back(r);
+    }
+    os << "static const casadi_int " << id << "[" << v.size() << "] = {";
+    for (size_t i = 0; i < v.size(); ++i) os << (i ? ", " : "") << v[i];
+    os << "};\n";
+  };
+  for (size_t i = 0; i < d.in.size(); ++i) sp_array(d.in[i].sparsity(), nm + "_s_in" + std::to_string(i));
+  for (size_t i = 0; i < d.out.size(); ++i) sp_array(d.out[i].sparsity(), nm + "_s_out" + std::to_string(i));
+  os << "\n/* " << nm << ":(";
+  for (size_t i = 0; i < d.in.size(); ++i) os << (i ? "," : "") << "i" << i << "[" << d.in[i].size1() << "x" << d.in[i].size2() << "]";
+  os << ")->(";
+  for (size_t i = 0; i < d.out.size(); ++i) os << (i ? "," : "") << "o" << i << "[" << d.out[i].size1() << "x" << d.out[i].size2() << "]";
+  os << ") */\n";
+  os << "static int " << nm << "_f" << index << "(const casadi_real** arg, casadi_real** res, casadi_int* iw, casadi_real* w, int mem) {\n";
+  for (const auto& c : d.consts) os << "  w[" << c.first << "] = " << c.second << ";\n";
+  for (size_t i = 0; i < d.in_w.size(); ++i)
+    for (size_t k = 0; k < d.in_w[i].size(); ++k)
+      if (d.in_w[i][k] >= 0) os << "  w[" << d.in_w[i][k] << "] = arg[" << i << "]? arg[" << i << "][" << k << "] : 0;\n";
+  for (const Data::Instr& t : d.tape) {
+    const std::string a = "w[" + std::to_string(t.a) + "]", b = t.b >= 0 ? "w[" + std::to_string(t.b) + "]" : std::string();
+    os << "  w[" << t.res << "] = " << c_expr(t.op, a, b) << ";\n";
+  }
+  for (size_t i = 0; i < d.out_w.size(); ++i)
+    for (size_t k = 0; k < d.out_w[i].size(); ++k)
+      os << "  if (res[" << i << "]!=0) res[" << i << "][" << k << "]=w[" << d.out_w[i][k] << "];\n";
+  os << "  return 0;\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT int " << nm << "(const casadi_real** arg, casadi_real** res, casadi_int* iw, casadi_real* w, int mem){\n"
+     << "  return " << nm << "_f" << index << "(arg, res, iw, w, mem);\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT int " << nm << "_alloc_mem(void) {\n  return 0;\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT int " << nm << "_init_mem(int mem) {\n  return 0;\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT void " << nm << "_free_mem(int mem) {\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT int " << nm << "_checkout(void) {\n  return 0;\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT void " << nm << "_release(int mem) {\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT void " << nm << "_incref(void) {\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT void " << nm << "_decref(void) {\n}\n\n";
+  os << "CASADI_SYMBOL_EXPORT casadi_int " << nm << "_n_in(void) { return " << d.in.size() << ";}\n\n";
+  os << "CASADI_SYMBOL_EXPORT casadi_int " << nm << "_n_out(void) { return " << d.out.size() << ";}\n\n";
+  os << "CASADI_SYMBOL_EXPORT casadi_real " << nm << "_default_in(casadi_int i) {\n  switch (i) {\n    default: return 0;\n  }\n}\n\n";
+  auto names = [&](const char* what, size_t count, char letter) {
+    os << "CASADI_SYMBOL_EXPORT const char* " << nm << "_name_" << what << "(casadi_int i) {\n  switch (i) {\n";
+    for (size_t i = 0; i < count; ++i) os << "    case " << i << ": return \"" << letter << i << "\";\n";
+    os << "    default: return 0;\n  }\n}\n\n";
+  };
+  names("in", d.in.size(), 'i');
+  names("out", d.out.size(), 'o');
+  auto sps = [&](const char* what, size_t count) {
+    os << "CASADI_SYMBOL_EXPORT const casadi_int* " << nm << "_sparsity_" << what << "(casadi_int i) {\n  switch (i) {\n";
+    for (size_t i = 0; i < count; ++i) os << "    case " << i << ": return " << nm << "_s_" << what << i << ";\n";
+    os << "    default: return 0;\n  }\n}\n\n";
+  };
+  sps("in", d.in.size());
+  sps("out", d.out.size());
+  os << "CASADI_SYMBOL_EXPORT int " << nm << "_work(casadi_int *sz_arg, casadi_int* sz_res, casadi_int *sz_iw, casadi_int *sz_w) {\n"
+     << "  if (sz_arg) *sz_arg = " << d.in.size() << ";\n  if (sz_res) *sz_res = " << d.out.size() << ";\n"
+     << "  if (sz_iw) *sz_iw = 0;\n  if (sz_w) *sz_w = " << d.nwork << ";\n  return 0;\n}\n\n";
+}
+
+void Function::generate(const std::string& filename) const {
+  casadi_assert(d_, "generate of a null Function");
+  CodeGenerator cg(filename);
+  cg.add(*this);
+  cg.generate();
+}
+
+std::string CodeGenerator::generate(const std::string& prefix) const {
+  std::string path = prefix + name_;
+  if (path.size() < 2 || path.substr(path.size() - 2) != ".c") path += ".c";
+  std::ofstream f(path);
+  casadi_assert(f.good(), "CodeGenerator: cannot open " + path);
+  std::string stem = name_;
+  const size_t slash = stem.find_last_of('/');
+  if (slash != std::string::npos) stem = stem.substr(slash + 1);
+  if (stem.size() > 2 && stem.substr(stem.size() - 2) == ".c") stem = stem.substr(0, stem.size() - 2);
+  char buf[4096];
+  std::snprintf(buf, sizeof(buf), kCHeader, stem.c_str());
+  f << buf;
+  for (size_t i = 0; i < fs_.size(); ++i) fs_[i].generate_body(f, static_cast<int>(i));
+  f << "\n#ifdef __cplusplus\n} /* extern \"C\" */\n#endif\n";
+  casadi_assert(f.good(), "CodeGenerator: write to " + path + " failed");
+  return path;
+}
+
 }  // namespace casadi

@@ -10,6 +10,7 @@
 
 #include "optimal_control_problem/OptimalControlProblem.h"
 #include "optimal_control_problem/sqp_solver/CuCaQP.h"
+#include "optimal_control_problem/codegen/StageCodegen.h"
 #include "problems/problems.h"
 
 namespace {
@@ -314,6 +315,37 @@ int ocp_host_compute_optimal_trajectory_batch(void* h, int B, const double* fram
 int ocp_host_problem_reset(void* h) {
   HOST_TRY
   static_cast<HostProblem*>(h)->ocp->resetWarmStart();
+  HOST_CATCH
+}
+
+// localSystemFunction + objective of a generated problem as ONE C file in CasADi's code-generator layout
+int ocp_host_problem_generate_c(void* h, const char* path) {
+  HOST_TRY
+  auto solver = static_cast<HostProblem*>(h)->ocp->getSolver();
+  if (!solver) throw std::runtime_error("genSolver() has not been called");
+  casadi::CodeGenerator cg(path);
+  cg.add(solver->getSXLocalSystemFunction());
+  cg.add(solver->getObjectiveFunction());
+  cg.generate();
+  HOST_CATCH
+}
+
+// CasADi-format C file -> stage library (CasadiCInterop.cpp); the library path is copied into out[cap]
+int ocp_host_compile_casadi_c(const char* c_file, const char* local_system_fn, const char* objective_fn, const char* name,
+                              int nf, int horizon, const char* code_dir, char* out, int cap) {
+  HOST_TRY
+  const std::string so = ocp_codegen::compile_casadi_c(c_file, local_system_fn, objective_fn, name, nf, horizon, code_dir, false);
+  if (static_cast<int>(so.size()) + 1 > cap) throw std::runtime_error("output buffer too small");
+  std::memcpy(out, so.c_str(), so.size() + 1);
+  HOST_CATCH
+}
+
+// devices of computeOptimalTrajectoryBatch (SQPOptimizationSolver::setDevices); n = 0 or 1: single device
+int ocp_host_problem_set_devices(void* h, const int* devices, int n) {
+  HOST_TRY
+  auto solver = static_cast<HostProblem*>(h)->ocp->getSolver();
+  if (!solver) throw std::runtime_error("genSolver() has not been called");
+  solver->setDevices(std::vector<int>(devices, devices + (n > 0 ? n : 0)));
   HOST_CATCH
 }
 
