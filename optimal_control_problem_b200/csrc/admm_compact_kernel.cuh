@@ -40,11 +40,12 @@ struct Layout {
   int s_stride, sp_stride, stage_stride;
   // slab
   size_t dinv, lsub, lp, q, l, u, D, E, pval, dx, dy, an, cn, sx, sz, sy, slab_doubles;
-  bool ok, q_smem, lu_smem;
+  bool ok, q_smem, lu_smem, scale_smem;
 };
 
-// flags: bit 0 = q in shared memory, bit 1 = l and u in shared memory (otherwise streamed from the slab)
-constexpr int kQInSmem = 1, kLuInSmem = 2;
+// flags: bit 0 = q in shared memory, bit 1 = l and u in shared memory, bit 2 = the scaling vectors D, E and the
+// Ruiz by-products in shared memory (otherwise streamed from the slab)
+constexpr int kQInSmem = 1, kLuInSmem = 2, kScaleInSmem = 4;
 __host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_words, int flags) {
   auto ev = [](size_t v) { return (v + 1) & ~size_t(1); };
   const size_t n = ev(P.n), m = ev(P.m), np = P.tri_np, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb;
@@ -69,20 +70,27 @@ __host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_wor
   L.xp = o; o += ev(np + 2);
   L.piv = o; o += 64;
   L.arena = o; o += ev((size_t(arena_words) + 1) / 2);
-  size_t qs = 0, ls = 0, us = 0;
+  size_t qs = 0, ls = 0, us = 0, ds = 0, es = 0, cns = 0;
   if (flags & kQInSmem) { qs = o; o += n; }
   if (flags & kLuInSmem) { ls = o; o += m; us = o; o += m; }
+  if (flags & kScaleInSmem) { ds = o; o += n; es = o; o += m; cns = o; o += n; }
   L.smem_doubles = o;
   size_t g = 0;
   L.dinv = g; g += nb * bs * ld; L.lsub = g; g += nb * bs * ld; L.lp = g; g += ev(np * nb * bs);
   L.q_smem = (flags & kQInSmem) != 0; L.lu_smem = (flags & kLuInSmem) != 0;
   if (L.q_smem) L.q = qs; else { L.q = g; g += n; }
   if (L.lu_smem) { L.l = ls; L.u = us; } else { L.l = g; g += m; L.u = g; g += m; }
-  L.D = g; g += n; L.E = g; g += m;
-  L.pval = g; g += ev(P.nnz_p); L.dx = g; g += n; L.dy = g; g += m; L.an = g; g += n; L.cn = g; g += n;
+  L.scale_smem = (flags & kScaleInSmem) != 0;
+  L.pval = g; g += ev(P.nnz_p); L.dx = g; g += n; L.dy = g; g += m;
+  if (L.scale_smem) {
+    L.D = ds; L.E = es; L.cn = cns;
+    L.an = L.x + m;   // behind the row scales on x|w: n_e + m_e - m >= n doubles are left there
+  } else {
+    L.D = g; g += n; L.E = g; g += m; L.an = g; g += n; L.cn = g; g += n;
+  }
   // parking space of a refactorisation: dx, dy and the Ruiz by-products are dead at that point
   L.sx = L.dx; L.sz = L.dy;
-  if (2 * n >= m) L.sy = L.an; else { L.sy = g; g += m; }
+  if (!L.scale_smem && 2 * n >= m) L.sy = L.an; else { L.sy = g; g += m; }
   L.slab_doubles = (g + 15) & ~size_t(15);
   return L;
 }
@@ -506,12 +514,13 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
   W.ring_bar = nullptr; W.ring_phase = nullptr; W.ring_slots = 0;
   W.Dinv = gl + L.dinv; W.Lsub = gl + L.lsub; W.Lp = gl + L.lp;
   W.q = (L.q_smem ? sm : gl) + L.q; W.l = (L.lu_smem ? sm : gl) + L.l; W.u = (L.lu_smem ? sm : gl) + L.u;
-  W.D = gl + L.D; W.E = gl + L.E;
+  W.D = (L.scale_smem ? sm : gl) + L.D; W.E = (L.scale_smem ? sm : gl) + L.E;
   W.Pval = gl + L.pval; W.dx = gl + L.dx; W.dy = gl + L.dy;
   W.idx = nullptr; W.phase = nullptr;
   uint32_t* ar = reinterpret_cast<uint32_t*>(sm + L.arena);
   for (int k = threadIdx.x; k < C.arena_words; k += kThreads) ar[k] = C.arena[k];
-  Ctx X{ar, sm + L.rscale, sm + L.psm, gl + L.an, gl + L.cn, gl + L.sx, gl + L.sz, gl + L.sy, gl + L.pval};
+  Ctx X{ar, sm + L.rscale, sm + L.psm, (L.scale_smem ? sm : gl) + L.an, (L.scale_smem ? sm : gl) + L.cn, gl + L.sx, gl + L.sz,
+        gl + L.sy, gl + L.pval};
   __syncthreads();
   Reducer R{red_buf, 0, (kThreads / 32) * kRedWidth};
   while (true) {

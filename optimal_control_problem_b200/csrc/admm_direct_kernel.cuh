@@ -85,7 +85,8 @@ __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
   const size_t n = P.n, m = P.m, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb, np = P.tri_np;
   switch (id) {
     case AR_X: case AR_Q: case AR_B: case AR_D: case AR_DX: return (n + 1) & ~size_t(1);
-    case AR_Z: case AR_Y: case AR_L: case AR_U: case AR_E: case AR_DY: case AR_W: return (m + 1) & ~size_t(1);
+    case AR_Z: case AR_Y: case AR_L: case AR_U: case AR_E: case AR_DY: return (m + 1) & ~size_t(1);
+    case AR_W: return ((m > n ? m : n) + 1) & ~size_t(1);   // also the Ruiz scratch of the n column norms (QP-only handles may have m < n)
     case AR_CTYPE: return (m + 7) / 8;
     case AR_AVAL: return (size_t(P.nnz_a) + 1) & ~size_t(1);
     case AR_PVAL: return (size_t(P.nnz_p) + 1) & ~size_t(1);

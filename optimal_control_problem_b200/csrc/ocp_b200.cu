@@ -505,7 +505,11 @@ int plan_launch(ocp_b200_solver* s) {
       CUDA_TRY(K::set_max_dynamic_smem(P.tri_bs, variant, max_optin - kc.static_smem));
       int best_flags = -1, best_occ = 0;
       size_t best_sm = 0, best_sl = 0;
-      for (int flags : {3, 1, 0}) {   // most shared memory first
+      // (kScaleInSmem -- D, E and the Ruiz by-products in shared memory as well -- was measured: 9.6 -> 9.9 ms per
+      //  launch on the H = 20 quadrotor, the 10 KB are worth more as L1; OCP_B200_COMPACT_FLAGS=7 selects it)
+      std::vector<int> flag_list{3, 1, 0};
+      if (const char* e = std::getenv("OCP_B200_COMPACT_FLAGS")) flag_list = {std::atoi(e) & 7};
+      for (int flags : flag_list) {   // most shared memory first
         size_t sm_d = 0, sl_d = 0;
         bool lay_ok = false;
         K::plan_sizes(P, s->cidx.arena_words, flags, &sm_d, &sl_d, &lay_ok);
