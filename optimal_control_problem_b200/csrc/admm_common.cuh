@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "ocp_b200.h"
 
@@ -17,6 +18,17 @@ constexpr int kRedWidth = 16;          // max values per block reduction
 constexpr int kMaxWarps = 32;
 
 typedef uint16_t idx_t;
+
+// -DOCP_B200_CANARY: every per-instance array (shared memory and slab) is followed by two guard doubles that the
+// kernels fill when they carve their state and verify when they leave; an overwritten guard is reported with
+// printf ("OCP_B200 CANARY ...").  compute-sanitizer is closed on the GPU pool this was developed on: this is the
+// bounds check of our own (tools/sanitize_cases.py runs every placement with it, profiles/r2_canary.txt).
+#ifdef OCP_B200_CANARY
+constexpr int kCanaryDoubles = 2;
+#else
+constexpr int kCanaryDoubles = 0;
+#endif
+__device__ __forceinline__ double canary_value(int id) { return __longlong_as_double(0x7ff4dead00000000LL + id); }
 
 // K-assembly program (direct kernel): one entry per structurally non-zero element of the bordered
 // block-tridiagonal K = P + sigma I + A' diag(rho) A that has to be computed, with the products

@@ -30,7 +30,12 @@ using direct::Rho;
 using direct::Work;
 
 // shared memory and slab layout (doubles); the same function runs on the host (plan) and on the device (carve)
+constexpr int kMaxGuards = 40;
 struct Layout {
+  // guard doubles behind every array (OCP_B200_CANARY builds): offsets, and whether they lie in the slab
+  int nguard;
+  size_t guard_off[kMaxGuards];
+  bool guard_slab[kMaxGuards];
   // shared
   size_t b, x, w, z, y, vend;       // iteration vectors; [b, vend) is also the set-up / factorisation scratch
   size_t aval, ctype, dp, xp, piv, arena, smem_doubles;
@@ -51,6 +56,9 @@ __host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_wor
   const size_t n = ev(P.n), m = ev(P.m), np = P.tri_np, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb;
   Layout L{};
   size_t o = 0;
+  auto guard = [&L](size_t& off, bool slab) {
+    if (kCanaryDoubles > 0 && L.nguard < kMaxGuards) { L.guard_off[L.nguard] = off; L.guard_slab[L.nguard] = slab; ++L.nguard; off += kCanaryDoubles; }
+  };
   L.b = o; o += n; L.x = o; o += n; L.w = o; o += m; L.z = o; o += m; L.y = o; o += m;
   const size_t vlen = o;
   L.s_stride = static_cast<int>(ev(bs * ld)); L.sp_stride = static_cast<int>(ev(np * bs)); L.stage_stride = L.s_stride;
@@ -61,36 +69,38 @@ __host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_wor
   L.stage = f; f += 4 * size_t(L.stage_stride);
   L.vend = f > vlen ? f : vlen;
   o = L.vend;
+  guard(o, false);
   L.rscale = L.x;   // m doubles on x|w
   L.psm = L.z;      // nnz_p doubles on z|y
   L.ok = ev(P.nnz_p) <= 2 * m && m <= n + m;
-  L.aval = o; o += ev(P.nnz_a);
-  L.ctype = o; o += ev((size_t(P.m) + 7) / 8);
-  L.dp = o; o += ev(np * (np + 1));
-  L.xp = o; o += ev(np + 2);
-  L.piv = o; o += 64;
-  L.arena = o; o += ev((size_t(arena_words) + 1) / 2);
+  L.aval = o; o += ev(P.nnz_a); guard(o, false);
+  L.ctype = o; o += ev((size_t(P.m) + 7) / 8); guard(o, false);
+  L.dp = o; o += ev(np * (np + 1)); guard(o, false);
+  L.xp = o; o += ev(np + 2); guard(o, false);
+  L.piv = o; o += 64; guard(o, false);
+  L.arena = o; o += ev((size_t(arena_words) + 1) / 2); guard(o, false);
   size_t qs = 0, ls = 0, us = 0, ds = 0, es = 0, cns = 0;
-  if (flags & kQInSmem) { qs = o; o += n; }
-  if (flags & kLuInSmem) { ls = o; o += m; us = o; o += m; }
-  if (flags & kScaleInSmem) { ds = o; o += n; es = o; o += m; cns = o; o += n; }
+  if (flags & kQInSmem) { qs = o; o += n; guard(o, false); }
+  if (flags & kLuInSmem) { ls = o; o += m; guard(o, false); us = o; o += m; guard(o, false); }
+  if (flags & kScaleInSmem) { ds = o; o += n; guard(o, false); es = o; o += m; guard(o, false); cns = o; o += n; guard(o, false); }
   L.smem_doubles = o;
   size_t g = 0;
-  L.dinv = g; g += nb * bs * ld; L.lsub = g; g += nb * bs * ld; L.lp = g; g += ev(np * nb * bs);
+  L.dinv = g; g += nb * bs * ld; guard(g, true); L.lsub = g; g += nb * bs * ld; guard(g, true); L.lp = g; g += ev(np * nb * bs); guard(g, true);
   L.q_smem = (flags & kQInSmem) != 0; L.lu_smem = (flags & kLuInSmem) != 0;
-  if (L.q_smem) L.q = qs; else { L.q = g; g += n; }
-  if (L.lu_smem) { L.l = ls; L.u = us; } else { L.l = g; g += m; L.u = g; g += m; }
+  if (L.q_smem) L.q = qs; else { L.q = g; g += n; guard(g, true); }
+  if (L.lu_smem) { L.l = ls; L.u = us; } else { L.l = g; g += m; guard(g, true); L.u = g; g += m; guard(g, true); }
   L.scale_smem = (flags & kScaleInSmem) != 0;
-  L.pval = g; g += ev(P.nnz_p); L.dx = g; g += n; L.dy = g; g += m;
+  L.pval = g; g += ev(P.nnz_p); guard(g, true); L.dx = g; g += n; guard(g, true); L.dy = g; g += m; guard(g, true);
   if (L.scale_smem) {
     L.D = ds; L.E = es; L.cn = cns;
     L.an = L.x + m;   // behind the row scales on x|w: n_e + m_e - m >= n doubles are left there
   } else {
-    L.D = g; g += n; L.E = g; g += m; L.an = g; g += n; L.cn = g; g += n;
+    L.D = g; g += n; guard(g, true); L.E = g; g += m; guard(g, true); L.an = g; g += n; guard(g, true); L.cn = g; g += n; guard(g, true);
   }
   // parking space of a refactorisation: dx, dy and the Ruiz by-products are dead at that point
   L.sx = L.dx; L.sz = L.dy;
-  if (!L.scale_smem && 2 * n >= m) L.sy = L.an; else { L.sy = g; g += m; }
+  if (!L.scale_smem && kCanaryDoubles == 0 && 2 * n >= m) L.sy = L.an;   // (an | cn are contiguous without guards)
+   else { L.sy = g; g += m; guard(g, true); }
   L.slab_doubles = (g + 15) & ~size_t(15);
   return L;
 }
@@ -519,6 +529,9 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
   W.idx = nullptr; W.phase = nullptr;
   uint32_t* ar = reinterpret_cast<uint32_t*>(sm + L.arena);
   for (int k = threadIdx.x; k < C.arena_words; k += kThreads) ar[k] = C.arena[k];
+  if (kCanaryDoubles > 0 && threadIdx.x == 0)
+    for (int gi = 0; gi < L.nguard; ++gi)
+      for (int c = 0; c < kCanaryDoubles; ++c) ((L.guard_slab[gi] ? gl : sm) + L.guard_off[gi])[c] = canary_value(gi);
   Ctx X{ar, sm + L.rscale, sm + L.psm, (L.scale_smem ? sm : gl) + L.an, (L.scale_smem ? sm : gl) + L.cn, gl + L.sx, gl + L.sz,
         gl + L.sy, gl + L.pval};
   __syncthreads();
@@ -533,6 +546,11 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
     solve_instance<BS>(P, C, S, A, W, X, R, inst, res);
     write_outputs(P, A, W.x, W.y, R, inst, res);
   }
+  if (kCanaryDoubles > 0 && threadIdx.x == 0)
+    for (int gi = 0; gi < L.nguard; ++gi)
+      for (int c = 0; c < kCanaryDoubles; ++c)
+        if (__double_as_longlong(((L.guard_slab[gi] ? gl : sm) + L.guard_off[gi])[c]) != __double_as_longlong(canary_value(gi)))
+          printf("OCP_B200 CANARY overwritten: compact kernel, guard %d (%s), CTA %d\n", gi, L.guard_slab[gi] ? "slab" : "shared", int(blockIdx.x));
 }
 
 }  // namespace compact

@@ -81,12 +81,21 @@ struct Work {
   double *D, *E, *dx, *dy;
 };
 
+__host__ __device__ inline size_t array_doubles_nominal(const PatternDev& P, int id);
 __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
+  const size_t sz = array_doubles_nominal(P, id);
+  return sz > 0 ? ((sz + 1) & ~size_t(1)) + kCanaryDoubles : 0;   // guard doubles behind every array (0 unless OCP_B200_CANARY)
+}
+__host__ __device__ inline size_t array_doubles_nominal(const PatternDev& P, int id) {
   const size_t n = P.n, m = P.m, bs = P.tri_bs, ld = P.tri_ld, nb = P.tri_nb, np = P.tri_np;
   switch (id) {
     case AR_X: case AR_Q: case AR_B: case AR_D: case AR_DX: return (n + 1) & ~size_t(1);
     case AR_Z: case AR_Y: case AR_L: case AR_U: case AR_E: case AR_DY: return (m + 1) & ~size_t(1);
+#ifdef OCP_B200_CANARY_SELFTEST   // negative control of the guard check: the round-2 bug (w sized m, written up to n) on purpose
+    case AR_W: return (m + 1) & ~size_t(1);
+#else
     case AR_W: return ((m > n ? m : n) + 1) & ~size_t(1);   // also the Ruiz scratch of the n column norms (QP-only handles may have m < n)
+#endif
     case AR_CTYPE: return (m + 7) / 8;
     case AR_AVAL: return (size_t(P.nnz_a) + 1) & ~size_t(1);
     case AR_PVAL: return (size_t(P.nnz_p) + 1) & ~size_t(1);
@@ -103,7 +112,7 @@ __host__ __device__ inline size_t array_doubles(const PatternDev& P, int id) {
 // With a compile-time placement (PLACE_SMEM / PLACE_MULTI) every pointer is derived from exactly
 // one base, so the compiler knows its address space and emits LDS/STS or LDG/STG, not generic LD.
 template <int kPlace>
-__device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t smem_mask, double* sm, double* gl) {
+__device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t smem_mask, double* sm, double* gl, bool check = false) {
   double* ptr[AR_COUNT];
 #pragma unroll
   for (int id = 0; id < AR_COUNT; ++id) {
@@ -111,6 +120,17 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
     const bool in_smem = kPlace == PLACE_SMEM ? true : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (kPlace == PLACE_BIG ? big_in_smem(id) : (smem_mask >> id & 1u) != 0));
     if (in_smem) { ptr[id] = sm; sm += sz; }
     else { ptr[id] = gl; gl += sz; }
+    if (kCanaryDoubles > 0 && sz > 0) {   // guard doubles at the end of the array's slot
+      double* g = (in_smem ? sm : gl) - kCanaryDoubles;
+      if (check) {
+        if (threadIdx.x == 0)
+          for (int c = 0; c < kCanaryDoubles; ++c)
+            if (__double_as_longlong(g[c]) != __double_as_longlong(canary_value(id)))
+              printf("OCP_B200 CANARY overwritten: direct kernel placement %d, array %d, CTA %d\n", kPlace, id, int(blockIdx.x));
+      } else if (threadIdx.x == 0) {
+        for (int c = 0; c < kCanaryDoubles; ++c) g[c] = canary_value(id);
+      }
+    }
   }
   W.x = ptr[AR_X]; W.q = ptr[AR_Q]; W.b = ptr[AR_B]; W.z = ptr[AR_Z]; W.y = ptr[AR_Y]; W.l = ptr[AR_L]; W.u = ptr[AR_U];
   W.ctype = reinterpret_cast<signed char*>(ptr[AR_CTYPE]);
@@ -1344,6 +1364,12 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
     QpResult res;
     solve_instance<kPlace>(PL, S, A, W, R, inst, res);
     write_outputs(P, A, W.x, W.y, R, inst, res);
+  }
+  if (kCanaryDoubles > 0) {
+    __syncthreads();
+    Work W2;
+    carve<kPlace>(W2, P, smem_mask, reinterpret_cast<double*>(smem_raw),
+                  kPlace == PLACE_SMEM ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles, true);
   }
 }
 

@@ -102,6 +102,14 @@ def test_python_cartpole_solves_like_cpp_cartpole(native):
     assert np.allclose(fa, fb, rtol=1e-9)
     for k in ("qp_status", "sqp_steps", "admm_iters", "checks"):
         assert np.array_equal(sa[:, native.STAT[k]], sb[:, native.STAT[k]]), k
+    # ... and against the CPU oracle, not only GPU against GPU: the Python-defined problem solves to the oracle's answer
+    import _oracle
+    ora = _oracle.OracleProblem("cartpole", horizon=H)
+    ora.set_qp_settings(_oracle.settings_from_b200(ocp.problem.get_settings()))
+    ox, of, ost = ora.solve_batch(frames, refs, x0=np.tile(frames, (1, H)))
+    assert np.abs(xa - ox).max() <= 1e-6 * max(1.0, np.abs(ox).max())
+    assert np.allclose(fa, of, rtol=1e-6, atol=1e-9)
+    assert np.array_equal(sa[:, native.STAT["admm_iters"]], ost[:, 2])
     # the class API of the reference's pybind module
     x1 = ocp.compute_optimal_trajectory(frames[0], refs[0])
     assert x1.shape == (5 * H,)
