@@ -7,7 +7,8 @@ definitions, casadi-lite symbolic layer) and nothing CUDA; the product never loa
 
 The reference itself (CasADi + OSQP v1.0.0.beta1 + OSQP-Eigen 0.9.0, none of them in
 /root/reference or in this image) cannot be compiled here, so there is no oracle/_ref:
-PARITY IS UNPINNED against the real OSQP; see the header of osqp_restate.hpp for what pins it.
+PARITY IS UNPINNED against the real OSQP; see the header of osqp_restate.hpp for what pins it and
+tools/pin_reference.py for the recipe that produces real-library fixtures elsewhere.
 """
 from __future__ import annotations
 

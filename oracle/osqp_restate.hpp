@@ -14,12 +14,14 @@
 //   reference's own test/test.cpp:13-185 (tests/test_oracle_kat.py), an independent
 //   active-set / dense-KKT cross-check in numpy (tests/test_oracle_qp.py), and the
 //   KKT-residual property tests.  Choices that upstream leaves to wall-clock time are made
-//   deterministic and documented where they occur.
+//   deterministic and documented where they occur.  tools/pin_reference.py produces OSQP /
+//   CasADi fixtures (tests/golden/ref_*.npz) on a machine that has the libraries;
+//   tests/test_reference_pins.py compares this file with them when they exist.
 //
 // Algorithm:
 //   setup : clamp l,u to +-1e30; Ruiz equilibration x`scaling` with cost normalisation;
 //           rho vector by constraint type; KKT = [[P+sigma I, A'],[A, -diag(1/rho)]] ordered
-//           by a minimum-degree heuristic, LDL' by the QDLDL up-looking algorithm.
+//           by approximate minimum degree (AMD), LDL' by the QDLDL up-looking algorithm.
 //   iterate: rhs = (sigma x - q, z - y/rho); solve; z~ = z + (nu - y)/rho;
 //           x+ = a x~ + (1-a) x;  z+ = clip(a z~ + (1-a) z + y/rho, l, u);
 //           y+ = y + rho (a z~ + (1-a) z - z+)                       (a = 1.6)
