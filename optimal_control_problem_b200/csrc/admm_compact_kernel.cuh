@@ -148,9 +148,248 @@ __device__ __forceinline__ void for_rows_A(const CompactIdx& C, const uint32_t* 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Tensor Memory as the home of the sweep blocks (BS = 16).
+//
+// The two sweeps of a solve are the sequential critical path, and with the factor in the L2 slab every stage
+// waits for a block row requested two stages earlier: ~900 cycles per stage at three CTAs per SM against ~200 in
+// isolation (profiles/r2_fine_phases.txt).  Shared memory is full -- but every SM also has 256 KB of Tensor Memory
+// that this FP64 path does not otherwise touch.  Each CTA allocates 128 columns (64 KB; 3-4 CTAs per SM fit into
+// the 512 columns) and keeps the sub-diagonal blocks there IN THE REGISTER LAYOUT OF THE SWEEP: a block is 16
+// columns, lane (row, half) of the owning warp holds its 8 doubles as 16 32-bit words, so one
+// tcgen05.ld.32x32b.x16 (latency ~ a shared-memory load, tools/micro/tmem_roundtrip.cu) delivers exactly the
+// operand of a stage.  A warp reaches only its own lane quadrant, so the four sweep chains go to four warps:
+//   warp 0  forward, top chain     slots 1 .. mid (row layout)         + the joining slot mid + 1
+//   warp 1  forward, bottom chain  slots nb-1 .. mid+2 (row layout)
+//   warp 2  backward, top chain    slots mid .. 1 (column layout)
+//   warp 3  backward, bottom chain slots mid+1 .. nb-1 (column layout)
+// A quadrant holds 8 blocks; the last (at most 3) stages of a chain are fetched from the slab into registers when
+// the sweep starts, so their latency hides behind the Tensor-Memory-fed stages.  The blocks are copied from the
+// slab after every factorisation (once per QP, or per rho update).
+// ---------------------------------------------------------------------------------------
+constexpr int kTmemCols = 128;          // per CTA; power of two
+constexpr int kTmemBlocks = kTmemCols / 16;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const double (&d)[8]) {
+  uint32_t v[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { v[2 * c] = __double2loint(d[c]); v[2 * c + 1] = __double2hiint(d[c]); }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, double (&d)[8]) {
+  uint32_t v[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < 8; ++c) d[c] = __hiloint2double(static_cast<int>(v[2 * c + 1]), static_cast<int>(v[2 * c]));
+}
+// (requesting the block of stage i + 1 before stage i is computed -- two register sets, the wait naming them as
+//  operands -- was measured: 8.8 -> 11.8 ms per launch at 96 registers; the load is as fast as a shared-memory one)
+
+// the chain of sweep stages one of the four sweep warps runs: stage i uses slot slot0 + i * dslot
+struct SweepChain { int slot0, dslot, dst0, src0, dblk, count; bool column; };
+__device__ __forceinline__ SweepChain sweep_chain(int warp, int nb) {
+  const int mid = nb / 2;
+  switch (warp) {
+    case 0: return SweepChain{1, 1, 1, 0, 1, mid, false};                               // y_k -= L_k y_{k-1}, k = 1..mid
+    case 1: return SweepChain{nb - 1, -1, nb - 2, nb - 1, -1, nb - 2 - mid, false};     // y_k -= U_k y_{k+1}, k = nb-2..mid+1
+    case 2: return SweepChain{mid, -1, mid - 1, mid, -1, mid, true};                    // x_k -= L_{k+1}' x_{k+1}, k = mid-1..0
+    default: return SweepChain{mid + 1, 1, mid + 1, mid, 1, nb - 1 - mid, true};        // x_k -= U_{k-1}' x_{k-1}, k = mid+1..nb-1
+  }
+}
+
+// this lane's 8 doubles of the block in `slot`, from the slab
+template <int BS, bool kColumn>
+__device__ __forceinline__ void slab_block_part(const double* Lsub, int slot, int lane, double (&dst)[8]) {
+  constexpr int ld = BS + 2, CPL = 8;
+  const int row = lane >> 1, half = lane & 1;
+  const double* p = Lsub + size_t(slot) * BS * ld + (kColumn ? size_t(half * CPL) * ld + row : size_t(row) * ld + half * CPL);
+  if (!kColumn) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < CPL / 2; ++i) { const double2 v = p2[i]; dst[2 * i] = v.x; dst[2 * i + 1] = v.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) dst[i] = p[i * ld];
+  }
+}
+
+// after a factorisation: every sweep warp copies the first kTmemBlocks blocks of its chain into its quadrant
+template <int BS>
+__device__ inline void tmem_publish(const Work& W, int nb, uint32_t tmem) {
+  static_assert(BS == 16, "one warp per chain, two lanes per block row");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 4) {
+    const SweepChain ch = sweep_chain(warp, nb);
+    const uint32_t base = tmem + (static_cast<uint32_t>(32 * warp) << 16);
+    const int ntm = ch.count < kTmemBlocks ? ch.count : kTmemBlocks;
+    for (int i = 0; i < ntm; ++i) {
+      double part[8];
+      if (ch.column) slab_block_part<BS, true>(W.Lsub, ch.slot0 + i * ch.dslot, lane, part);
+      else slab_block_part<BS, false>(W.Lsub, ch.slot0 + i * ch.dslot, lane, part);
+      tmem_st16(base + 16 * i, part);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+// one chain: Tensor-Memory-fed stages first, then the (at most three) stages whose block rows were requested from
+// the slab when the sweep started, then -- chains longer than that -- plain slab loads
+template <int BS, bool kColumn>
+__device__ __forceinline__ void run_chain_tmem(const Work& W, double* bx, const SweepChain& ch, uint32_t base, int lane) {
+  constexpr int CPL = 8;
+  const int row = lane >> 1, half = lane & 1;
+  const bool writer = half == 0;
+  const int ntm = ch.count < kTmemBlocks ? ch.count : kTmemBlocks;
+  const int nreg = ch.count - ntm < 3 ? ch.count - ntm : 3;
+  double Ra[CPL], Rb[CPL], Rc[CPL];
+  if (nreg > 0) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + ntm * ch.dslot, lane, Ra);
+  if (nreg > 1) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + (ntm + 1) * ch.dslot, lane, Rb);
+  if (nreg > 2) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + (ntm + 2) * ch.dslot, lane, Rc);
+  const int db = ch.dblk * BS;
+  const double* srcp = bx + ch.src0 * BS + half * CPL;
+  double* dstp = bx + ch.dst0 * BS + row;
+  for (int i = 0; i < ntm; ++i) {
+    double L[CPL];
+    tmem_ld16(base + 16 * i, L);
+    direct::sweep_stage<BS>(L, srcp, dstp, writer);
+    srcp += db; dstp += db;
+  }
+  if (nreg > 0) { direct::sweep_stage<BS>(Ra, srcp, dstp, writer); srcp += db; dstp += db; }
+  if (nreg > 1) { direct::sweep_stage<BS>(Rb, srcp, dstp, writer); srcp += db; dstp += db; }
+  if (nreg > 2) { direct::sweep_stage<BS>(Rc, srcp, dstp, writer); srcp += db; dstp += db; }
+  for (int i = ntm + nreg; i < ch.count; ++i) {
+    double L[CPL];
+    slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + i * ch.dslot, lane, L);
+    direct::sweep_stage<BS>(L, srcp, dstp, writer);
+    srcp += db; dstp += db;
+  }
+}
+
+// K x = b in place (b = [p | block 0 | ... | block nb-1]): direct::tri_solve_twisted with the sweeps fed from Tensor Memory
+template <int BS>
+__device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W, uint32_t tmem) {
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int np = P.tri_np, nb = P.tri_nb, N = nb * BS;
+  constexpr int ld = BS + 2;
+  const int mid = nb / 2;
+  double* bx = W.b + np;
+  OCP_B200_FINE_CLOCK(clk, W.phase);
+  const uint32_t base = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
+  // the warps that idle during the forward sweep fetch their D_k^-1 row of the first diagonal pass now
+  const int dTb = (T / BS) * BS;
+  const bool pre = warp >= 2 && tid < dTb && tid < N;
+  double drow[BS];
+  if (pre) {
+    const double2* p2 = reinterpret_cast<const double2*>(W.Dinv + size_t(tid / BS) * BS * ld + (tid % BS) * ld);
+#pragma unroll
+    for (int i = 0; i < BS / 2; ++i) { const double2 v = p2[i]; drow[2 * i] = v.x; drow[2 * i + 1] = v.y; }
+  }
+  // forward: both chains at once (warps 0 and 1), then the second contribution to block mid; the block row of that
+  // joining slot is requested from the slab before warp 0 starts its chain
+  double Lj[8];
+  if (warp == 0 && mid + 1 < nb) slab_block_part<BS, false>(W.Lsub, mid + 1, lane, Lj);
+  if (warp < 2) run_chain_tmem<BS, false>(W, bx, sweep_chain(warp, nb), base, lane);
+  __syncthreads();
+  if (warp == 0 && mid + 1 < nb) direct::sweep_stage<BS>(Lj, bx + (mid + 1) * BS + (lane & 1) * 8, bx + mid * BS + (lane >> 1), (lane & 1) == 0);
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
+  // border: y_p = b_p - sum_k L_pk y_k, x_p = D_p^-1 y_p   (as in direct::tri_solve_twisted)
+  if (np > 0) {
+    const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
+    for (int r0 = 0; r0 < np; r0 += nhw) {
+      const int r = r0 + hw;
+      const bool have = r < np;
+      const double* rowp = W.Lp + size_t(have ? r : 0) * N;
+      double s0 = 0.0, s1 = 0.0;
+      for (int j0 = hl; j0 < N; j0 += 128) {
+        double lv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 16 * u;
+          const bool ok = have && j < N;
+          lv[u] = ok ? rowp[j] : 0.0;
+          yv[u] = ok ? bx[j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) { s0 = fma(lv[u], yv[u], s0); s1 = fma(lv[u + 1], yv[u + 1], s1); }
+      }
+      double s = s0 + s1;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (have && hl == 0) W.xp[r] = W.b[r] - s;
+    }
+    __syncthreads();
+    if (tid < np) {
+      double s0 = 0.0, s1 = 0.0;
+      int c = 0;
+      for (; c + 1 < np; c += 2) {
+        s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
+        s1 = fma(W.Dp[tid * (np + 1) + c + 1], W.xp[c + 1], s1);
+      }
+      if (c < np) s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
+      W.b[tid] = s0 + s1;
+    }
+    __syncthreads();
+  }
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
+  // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
+  {
+    const int Tb = (T / BS) * BS;
+    const int k1 = tid / BS, r1 = tid % BS, kstep = T / BS;
+    for (int base_j = 0, k = k1; base_j < N; base_j += Tb, k += kstep) {
+      const int j = tid < Tb ? base_j + tid : N;
+      double v = 0.0;
+      if (j < N) {
+        if (pre && base_j == 0) {
+          const double* yk = bx + k * BS;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+          for (int t = 0; t < BS; t += 4) {
+            s0 = fma(drow[t], yk[t], s0); s1 = fma(drow[t + 1], yk[t + 1], s1);
+            s2 = fma(drow[t + 2], yk[t + 2], s2); s3 = fma(drow[t + 3], yk[t + 3], s3);
+          }
+          v = (s0 + s1) + (s2 + s3);
+        } else {
+          v = direct::dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
+        }
+        double v1 = 0.0;
+        if (np == 12) {   // the border size of a 12-state reference: all loads issued before the first FMA
+          double lv[12];
+#pragma unroll
+          for (int p = 0; p < 12; ++p) lv[p] = W.Lp[size_t(p) * N + j];
+#pragma unroll
+          for (int p = 0; p < 12; p += 2) { v = fma(-lv[p], W.b[p], v); v1 = fma(-lv[p + 1], W.b[p + 1], v1); }
+        } else {
+          int p = 0;
+          for (; p + 1 < np; p += 2) {
+            v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+            v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
+          }
+          if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+        }
+        v += v1;
+      }
+      __syncthreads();
+      if (j < N) bx[j] = v;
+    }
+  }
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_DIAG);
+  // backward, from block mid outwards: warps 2 and 3 (their quadrants hold the column layout)
+  if (warp == 2 || warp == 3) run_chain_tmem<BS, true>(W, bx, sweep_chain(warp, nb), base, lane);
+  __syncthreads();
+  OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
+}
+
 template <int BS>
 __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, const ocp_b200_settings& S, const SolveArgs& A,
-                                      Work& W, const Ctx& X, Reducer& R, int inst, QpResult& out) {
+                                      Work& W, const Ctx& X, Reducer& R, int inst, QpResult& out, uint32_t tmem) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int n = P.n, m = P.m;
   const double sigma = S.sigma, relax = S.relax;
@@ -280,6 +519,7 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
   direct::tri_assemble_program(P, W, rv, sigma);
   clk.lap(OCP_B200_PHASE_KKT_ASSEMBLE);
   direct::tri_factor_twisted<BS>(P, W);   // scratch: the iteration vectors (nothing lives there yet)
+  if constexpr (BS == 16) tmem_publish<BS>(W, P.tri_nb, tmem);
   clk.lap(OCP_B200_PHASE_FACTOR);
   // ---- cold start ----
   for (int j = tid; j < n; j += T) W.x[j] = 0.0;
@@ -300,7 +540,8 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
     }
     __syncthreads();
     clk.lap(OCP_B200_PHASE_RHS);
-    direct::tri_solve_twisted<BS>(P, W);   // b <- x~
+    if constexpr (BS == 16) tri_solve_twisted_tmem<BS>(P, W, tmem);   // b <- x~
+    else direct::tri_solve_twisted<BS>(P, W);
     ++solves;
     clk.lap(OCP_B200_PHASE_SOLVE);
 
@@ -481,6 +722,7 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
         // 9.6 -> 9.8 ms per launch with P and W passed by value, 11.7 ms by reference)
         direct::tri_assemble_program(P, W, rv, sigma);
         direct::tri_factor_twisted<BS>(P, W);
+        if constexpr (BS == 16) tmem_publish<BS>(W, P.tri_nb, tmem);
         for (int j = tid; j < n; j += T) W.x[j] = X.sx[j];
         for (int i = tid; i < m; i += T) {
           const double zi = X.sz[i], yi = X.sy[i];
@@ -512,6 +754,19 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red_buf[2 * (kThreads / 32) * kRedWidth];
   __shared__ int s_inst;
+  __shared__ uint32_t s_tmem;
+  static_assert(kThreads >= 128, "four sweep warps");
+  if constexpr (BS == 16) {   // Tensor Memory for the sweep blocks: one warp allocates, the same warp frees it at the end
+    if (threadIdx.x < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&s_tmem))), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const uint32_t tmem = BS == 16 ? s_tmem : 0u;
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* gl = A.slab + size_t(blockIdx.x) * A.slab_doubles;
   const Layout L = make_layout(P, C.arena_words, layout_flags);
@@ -543,8 +798,13 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
     __syncthreads();
     if (inst >= A.B) break;
     QpResult res;
-    solve_instance<BS>(P, C, S, A, W, X, R, inst, res);
+    solve_instance<BS>(P, C, S, A, W, X, R, inst, res, tmem);
     write_outputs(P, A, W.x, W.y, R, inst, res);
+  }
+  if constexpr (BS == 16) {
+    __syncthreads();
+    if (threadIdx.x < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
   }
   if (kCanaryDoubles > 0 && threadIdx.x == 0)
     for (int gi = 0; gi < L.nguard; ++gi)

@@ -514,12 +514,23 @@ int plan_launch(ocp_b200_solver* s) {
         bool lay_ok = false;
         K::plan_sizes(P, s->cidx.arena_words, flags, &sm_d, &sl_d, &lay_ok);
         if (!lay_ok || sm_d * sizeof(double) + kc.static_smem > size_t(max_optin)) continue;
+        // residency by hand: the occupancy calculator answers 1 for a kernel that allocates Tensor Memory (it cannot know
+        // how many of the 512 columns a CTA will ask for); the compact kernel takes 128 of them when BS == 16
         int occ = 0;
-        CUDA_TRY(K::occupancy(P.tri_bs, variant, static_cast<int>(sm_d * sizeof(double)), &occ));
+        {
+          int smem_sm = 0, regs_sm = 0;
+          CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device));
+          CUDA_TRY(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, s->device));
+          const int regs_cta = ((kc.regs + 7) / 8 * 8) * kc.threads;
+          const size_t smem_cta = sm_d * sizeof(double) + kc.static_smem + 1024;   // 1 KB reserved per CTA
+          occ = std::min({regs_sm / std::max(1, regs_cta), static_cast<int>(size_t(smem_sm) / smem_cta), 2048 / kc.threads,
+                          P.tri_bs == 16 ? 512 / 128 : 32});
+        }
         if (occ > best_occ && best_occ < target) { best_occ = occ; best_flags = flags; best_sm = sm_d; best_sl = sl_d; }
       }
       if (best_flags >= 0) {
         int occ = std::min(best_occ, target);
+        if (const char* f = std::getenv("OCP_B200_FORCE_CTAS_PER_SM")) occ = std::max(1, std::atoi(f));   // experiment: ignore the occupancy calculator
         if (const char* cap = std::getenv("OCP_B200_MAX_CTAS_PER_SM")) occ = std::min(occ, std::max(1, std::atoi(cap)));
         if (occ * kc.threads > (s->wide.max_ctas / s->num_sms) * s->wide.threads || env) {
           s->wide.place = 4; s->wide.threads = kc.threads; s->wide.smem_bytes = static_cast<int>(best_sm * sizeof(double));
