@@ -497,8 +497,10 @@ int plan_launch(ocp_b200_solver* s) {
     s->compact_variant = 0; s->compact_flags = 0;
     if (s->compact_ok && (P.tri_bs == 16 || P.tri_bs == 20) && P.tri_ld == P.tri_bs + 2 && (!env || !std::strcmp(env, "compact"))) {
       namespace K = ocpb200::compact;
-      int variant = 1;   // measured on the H = 20 quadrotor: both shapes 9.6 ms per launch; 192x3 keeps 64 MB of slabs in L2, 128x4 91 MB
-      if (const char* e = std::getenv("OCP_B200_COMPACT_VARIANT")) variant = !std::strcmp(e, "128x4") ? 0 : 1;
+      // measured on the H = 20 quadrotor: 9.6 ms per launch for both shapes with the sweep blocks in the L2 slab; with
+      // them in Tensor Memory 128x4 (8.55 ms) is ahead of 192x3 (8.84 ms)
+      int variant = 0;
+      if (const char* e = std::getenv("OCP_B200_COMPACT_VARIANT")) variant = !std::strcmp(e, "192x3") ? 1 : 0;
       const int target = variant == 0 ? 4 : 3;
       D::KernelInfo kc{};
       CUDA_TRY(K::kernel_info(P.tri_bs, variant, &kc));
