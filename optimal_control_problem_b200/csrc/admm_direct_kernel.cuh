@@ -210,20 +210,37 @@ __device__ inline void tri_assemble_program(const PatternDev& P, const Work& W, 
   }
   __syncthreads();
   double* const arr[4] = {W.Dinv, W.Lsub, W.Lp, W.Dp};
-  for (int e = tid; e < P.kprog_entries; e += T) {
-    const KEntry ent = P.kprog[e];
-    double s = ent.diag ? sigma : 0.0;
-    if (ent.ppos >= 0) s += W.Pval[ent.ppos];
-    for (int q = 0; q < ent.nruns; ++q) {
-      const KRun run = P.kruns[ent.run_begin + q];
-#pragma unroll 4
-      for (int t = 0; t < run.len; ++t) {
-        const int ka = run.ka + t, kc = run.kc + t;
-        s += rho.of(W.ctype[run.row0 + t]) * W.Aval[ka] * W.Aval[kc];
-      }
+  // The program lives in global memory (L2): an entry and its first run are two DEPENDENT loads, ~2 L2 round trips per
+  // element if taken one at a time (the loop was bound by exactly that: 124 k cycles per QP at four CTAs per SM).  Four
+  // elements per thread are fetched together -- four independent entry loads, then four independent run loads --
+  // and computed in the old order, so every sum is bit-identical.
+  constexpr int kBatch = 4;
+  for (int e0 = tid; e0 < P.kprog_entries; e0 += kBatch * T) {
+    KEntry ent[kBatch];
+    KRun first[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + u * T;
+      ent[u] = P.kprog[e < P.kprog_entries ? e : e0];
     }
-    arr[ent.dest0 >> 30][ent.dest0 & 0x3fffffffu] = s;
-    if (ent.dest1 != 0xffffffffu) arr[ent.dest1 >> 30][ent.dest1 & 0x3fffffffu] = s;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) first[u] = P.kruns[ent[u].nruns > 0 ? ent[u].run_begin : 0];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (e0 + u * T >= P.kprog_entries) continue;
+      double s = ent[u].diag ? sigma : 0.0;
+      if (ent[u].ppos >= 0) s += W.Pval[ent[u].ppos];
+      for (int q = 0; q < ent[u].nruns; ++q) {
+        const KRun run = q == 0 ? first[u] : P.kruns[ent[u].run_begin + q];
+#pragma unroll 4
+        for (int t = 0; t < run.len; ++t) {
+          const int ka = run.ka + t, kc = run.kc + t;
+          s += rho.of(W.ctype[run.row0 + t]) * W.Aval[ka] * W.Aval[kc];
+        }
+      }
+      arr[ent[u].dest0 >> 30][ent[u].dest0 & 0x3fffffffu] = s;
+      if (ent[u].dest1 != 0xffffffffu) arr[ent[u].dest1 >> 30][ent[u].dest1 & 0x3fffffffu] = s;
+    }
   }
   __syncthreads();
 }
