@@ -41,7 +41,7 @@ struct Layout {
   size_t aval, ctype, dp, xp, piv, arena, smem_doubles;
   // overlays of [b, vend)
   size_t rscale, psm;               // Ruiz: row scales on x|w, P values on z|y   (column scales are b itself)
-  size_t dp2, s, sp, stage;         // factorisation scratch
+  size_t dp2, s, sp, stage, fb;     // factorisation scratch (fb: the L_p tiles of the chain steps)
   int s_stride, sp_stride, stage_stride;
   // slab
   size_t dinv, lsub, lp, q, l, u, D, E, pval, dx, dy, an, cn, sx, sz, sy, slab_doubles;
@@ -67,6 +67,7 @@ __host__ __device__ inline Layout make_layout(const PatternDev& P, int arena_wor
   L.s = f; f += 2 * size_t(L.s_stride);
   L.sp = f; f += 2 * size_t(L.sp_stride);
   L.stage = f; f += 4 * size_t(L.stage_stride);
+  L.fb = f; f += 2 * size_t(L.sp_stride);
   L.vend = f > vlen ? f : vlen;
   o = L.vend;
   guard(o, false);
@@ -774,7 +775,7 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
   W.b = sm + L.b; W.x = sm + L.x; W.w = sm + L.w; W.z = sm + L.z; W.y = sm + L.y;
   W.Aval = sm + L.aval; W.ctype = reinterpret_cast<signed char*>(sm + L.ctype);
   W.Dp = sm + L.dp; W.xp = sm + L.xp; W.piv = sm + L.piv;
-  W.Dp2 = sm + L.dp2; W.S = sm + L.s; W.Sp = sm + L.sp; W.stage = sm + L.stage;
+  W.Dp2 = sm + L.dp2; W.S = sm + L.s; W.Sp = sm + L.sp; W.stage = sm + L.stage; W.Fb = sm + L.fb;
   W.s_stride = L.s_stride; W.sp_stride = L.sp_stride; W.stage_stride = L.stage_stride;
   W.ring_bar = nullptr; W.ring_phase = nullptr; W.ring_slots = 0;
   W.Dinv = gl + L.dinv; W.Lsub = gl + L.lsub; W.Lp = gl + L.lp;

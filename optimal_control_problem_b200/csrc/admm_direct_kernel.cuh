@@ -75,6 +75,7 @@ struct Work {
   unsigned* ring_phase;
   int ring_slots;   // per chain; 0 = no ring
   double *Lp, *Dp, *Dp2, *S, *Sp, *xp, *piv;   // border: L_pk [np x N], D_p^-1 [np x (np+1)], scratch (two sets)
+  double* Fb;   // optional: two [np x bs] shared-memory tiles holding the L_p block a chain step just finished (null: read it back from L_p)
   int s_stride, sp_stride;
   long long* phase;   // cycle counters of CTA 0 (null unless profiling)
   double *w;                        // rho .* z - y, kept current by the update phase
@@ -150,6 +151,7 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
   W.Sp = bp; bp += 2 * W.sp_stride;
   W.xp = bp; bp += (np + 2) & ~size_t(1);
   W.piv = bp;
+  W.Fb = nullptr;
   W.w = ptr[AR_W];
   W.D = ptr[AR_D]; W.E = ptr[AR_E]; W.dx = ptr[AR_DX]; W.dy = ptr[AR_DY];
 }

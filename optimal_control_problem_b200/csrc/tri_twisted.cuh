@@ -27,7 +27,7 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 // Updates D_k (not inverted here), V_k, finalises L_p,pred, accumulates into Dpacc, overwrites the slot.
 template <int BS, bool kTop>
 __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*ld*/, int k, int pred, int slot, double* S,
-                                           double* Sp, double* Dpacc, int gt, int GT, int bar, double* stage) {
+                                           double* Sp, double* Dpacc, int gt, int GT, int bar, double* stage, double* F = nullptr) {
   constexpr int bb = BS * BS, ld = BS + 2;   // compile-time pitch: addresses fold into immediates
   const int pb = np * BS;
   double* Cg = W.Lsub + size_t(slot) * BS * ld;
@@ -67,12 +67,14 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
     const double f = dot_cc<BS>(Sp + r * BS, Dm + c * ld);
     W.Lp[size_t(r) * N + k * BS + c] -= s;
     W.Lp[size_t(r) * N + pred * BS + c] = f;
+    if (F != nullptr) F[e] = f;   // shared-memory copy of L_p,pred for the accumulation below (L_p may live in the slab)
   }
   group_barrier(bar, GT);
   // D_p accumulator += V_pred L_p,pred';  slot <- coupling
   for (int e = gt; e < np * np; e += GT) {
     const int r = e / np, c = e - r * np;
-    Dpacc[r * (np + 1) + c] += dot_cs<BS>(Sp + r * BS, W.Lp + size_t(c) * N + pred * BS, 1);
+    Dpacc[r * (np + 1) + c] += F != nullptr ? dot_cc<BS>(Sp + r * BS, F + c * BS)
+                                            : dot_cs<BS>(Sp + r * BS, W.Lp + size_t(c) * N + pred * BS, 1);
   }
   for (int e = gt; e < bb; e += GT) {
     const int r = e / BS, c = e % BS;
@@ -94,6 +96,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   double* piv = W.piv + grp * 32;
   double* Dpacc = W.Dp2 + grp * np * (np + 1);
   double* stage = W.stage ? W.stage + grp * 2 * W.stage_stride : nullptr;
+  double* F = W.Fb ? W.Fb + grp * W.sp_stride : nullptr;   // shared-memory copy of the L_p block just finished (optional)
   for (int e = gt; e < np * (np + 1); e += GT) Dpacc[e] = 0.0;
   // both chains: invert the chain's current block, then eliminate into the next one
   if (grp == 0) {
@@ -102,14 +105,14 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(1, GT);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_INVERT);
-      chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage);
+      chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage, F);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_STEP);
     }
   } else {
     for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(2, GT);
-      chain_step<BS, false>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage);
+      chain_step<BS, false>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage, F);
     }
     if (mid + 1 < nb) {                       // block mid+1: inverted here, eliminated into mid below
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid + 1) * BS * ld, ld, lane, piv);
@@ -118,7 +121,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   }
   __syncthreads();
   // the bottom chain's last step lands on block mid as well: run it with the whole CTA
-  if (mid + 1 < nb) chain_step<BS, false>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage);
+  if (mid + 1 < nb) chain_step<BS, false>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage, W.Fb);
   if (tid < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid) * BS * ld, ld, lane, W.piv);
   __syncthreads();
   // border of the last block, then D_p = K_pp - (accumulated) - V_mid L_p,mid', inverted
@@ -132,14 +135,17 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
     __syncthreads();
     for (int e = tid; e < pb; e += T) {
       const int r = e / BS, c = e % BS;
-      W.Lp[size_t(r) * N + mid * BS + c] = dot_cc<BS>(W.Sp + r * BS, Dm + c * ld);
+      const double f = dot_cc<BS>(W.Sp + r * BS, Dm + c * ld);
+      W.Lp[size_t(r) * N + mid * BS + c] = f;
+      if (W.Fb != nullptr) W.Fb[e] = f;
     }
     __syncthreads();
     for (int e = tid; e < np * np; e += T) {
       const int r = e / np, c = e - r * np;
       const int o = r * (np + 1) + c;
       W.Dp[o] -= W.Dp2[o] + W.Dp2[np * (np + 1) + o] +
-                 dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + mid * BS, 1);
+                 (W.Fb != nullptr ? dot_cc<BS>(W.Sp + r * BS, W.Fb + c * BS)
+                                  : dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + mid * BS, 1));
     }
     __syncthreads();
     if (tid < 32) invert_border(W.Dp, np, lane, W.piv);
