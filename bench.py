@@ -445,7 +445,7 @@ def b200_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_sample or (max(64, 64 * threads) if PROBLEM == "quadrotor" else 2 * threads)   # ~20 core-seconds
+        sample = args.cpu_sample or (max(64, 128 * threads) if PROBLEM == "quadrotor" else 2 * threads)   # ~25 core-seconds
         t = cpu_run(sample, threads, repeats=1, warmup=0)[0]
         t1 = cpu_run(min(sample, 32), 1, repeats=1, warmup=0)[0] / min(sample, 32)
         p50_1t = cpu_latency_p50(200 if PROBLEM == "quadrotor" else 8)

@@ -96,7 +96,8 @@ def cuda_lib() -> C.CDLL:
     """``libocp_b200.so`` -- raises (never falls back) when it has not been built."""
     global _cuda
     if _cuda is None:
-        path = _PKG / "lib" / "libocp_b200.so"
+        # OCP_B200_LIB_DIR: another build of the two libraries (A/B measurements of kernel variants in one GPU session)
+        path = Path(os.environ.get("OCP_B200_LIB_DIR", _PKG / "lib")) / "libocp_b200.so"
         if not path.exists():
             raise NativeLibraryMissing(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
         lib = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
@@ -138,7 +139,7 @@ def host_lib() -> C.CDLL:
     global _host
     if _host is None:
         cuda_lib()
-        path = _PKG / "lib" / "libocp_b200_host.so"
+        path = Path(os.environ.get("OCP_B200_LIB_DIR", _PKG / "lib")) / "libocp_b200_host.so"
         if not path.exists():
             raise NativeLibraryMissing(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
         lib = C.CDLL(str(path))
