@@ -200,6 +200,7 @@ struct PhaseClock {
   }
 };
 
+
 // The finer split of the solve / factor phases costs a predicated branch per lap in every thread;
 // it is compiled in only with -DOCP_B200_FINE_PHASES (tools/phase_profile.py documents the numbers).
 #ifdef OCP_B200_FINE_PHASES

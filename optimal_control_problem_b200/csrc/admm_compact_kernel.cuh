@@ -302,6 +302,12 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
   // border: y_p = b_p - sum_k L_pk y_k, x_p = D_p^-1 y_p   (as in direct::tri_solve_twisted)
   if (np > 0) {
+    const int nw = T >> 5;
+    if (direct::border_rows_by_warp(np, N, nw)) {
+      // whole warps per border row (3 or 2 rows each), every slab load of a warp issued before its first FMA:
+      // one L2 round trip for the phase instead of one per 128-column chunk and row pass
+      direct::border_rows_dispatch<true>(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
+    } else {
     const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
     for (int r0 = 0; r0 < np; r0 += nhw) {
       const int r = r0 + hw;
@@ -325,6 +331,7 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
       for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (have && hl == 0) W.xp[r] = W.b[r] - s;
     }
+    }
     __syncthreads();
     if (tid < np) {
       double s0 = 0.0, s1 = 0.0;
@@ -341,43 +348,70 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
   // diagonal: c_k = D_k^-1 y_k - L_pk' x_p   (in place: value computed, barrier, stored)
   {
+    // up to kPass passes of T rows are computed before the one barrier that protects the in-place store, so the slab
+    // loads of a later pass are in flight while the earlier pass multiplies
+#ifndef OCP_B200_DIAG_PASSES
+#define OCP_B200_DIAG_PASSES 1
+#endif
+    constexpr int kPass = OCP_B200_DIAG_PASSES;
     const int Tb = (T / BS) * BS;
     const int k1 = tid / BS, r1 = tid % BS, kstep = T / BS;
-    for (int base_j = 0, k = k1; base_j < N; base_j += Tb, k += kstep) {
-      const int j = tid < Tb ? base_j + tid : N;
-      double v = 0.0;
-      if (j < N) {
-        if (pre && base_j == 0) {
-          const double* yk = bx + k * BS;
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int base0 = 0, k0 = k1; base0 < N; base0 += kPass * Tb, k0 += kPass * kstep) {
+      double vq[kPass];
 #pragma unroll
-          for (int t = 0; t < BS; t += 4) {
-            s0 = fma(drow[t], yk[t], s0); s1 = fma(drow[t + 1], yk[t + 1], s1);
-            s2 = fma(drow[t + 2], yk[t + 2], s2); s3 = fma(drow[t + 3], yk[t + 3], s3);
+      for (int q = 0; q < kPass; ++q) {
+        const int base_j = base0 + q * Tb, k = k0 + q * kstep;
+        const int j = tid < Tb ? base_j + tid : N;
+        double v = 0.0;
+        if (j < N) {
+          if (pre && base_j == 0) {
+            const double* yk = bx + k * BS;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int t = 0; t < BS; t += 4) {
+              s0 = fma(drow[t], yk[t], s0); s1 = fma(drow[t + 1], yk[t + 1], s1);
+              s2 = fma(drow[t + 2], yk[t + 2], s2); s3 = fma(drow[t + 3], yk[t + 3], s3);
+            }
+            v = (s0 + s1) + (s2 + s3);
+          } else {
+            const double2* d2 = reinterpret_cast<const double2*>(W.Dinv + size_t(k) * BS * ld + r1 * ld);
+            const double* yk = bx + k * BS;
+            double dr[BS];
+#pragma unroll
+            for (int t = 0; t < BS / 2; ++t) { const double2 x = d2[t]; dr[2 * t] = x.x; dr[2 * t + 1] = x.y; }
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int t = 0; t < BS; t += 4) {
+              s0 = fma(dr[t], yk[t], s0); s1 = fma(dr[t + 1], yk[t + 1], s1);
+              s2 = fma(dr[t + 2], yk[t + 2], s2); s3 = fma(dr[t + 3], yk[t + 3], s3);
+            }
+            v = (s0 + s1) + (s2 + s3);
           }
-          v = (s0 + s1) + (s2 + s3);
-        } else {
-          v = direct::dot_cs<BS>(W.Dinv + size_t(k) * BS * ld + r1 * ld, bx + k * BS, 1);
-        }
-        double v1 = 0.0;
-        if (np == 12) {   // the border size of a 12-state reference: all loads issued before the first FMA
-          double lv[12];
+          double v1 = 0.0;
+          if (np == 12) {   // the border size of a 12-state reference: all loads issued before the first FMA
+            double lv[12];
 #pragma unroll
-          for (int p = 0; p < 12; ++p) lv[p] = W.Lp[size_t(p) * N + j];
+            for (int p = 0; p < 12; ++p) lv[p] = W.Lp[size_t(p) * N + j];
 #pragma unroll
-          for (int p = 0; p < 12; p += 2) { v = fma(-lv[p], W.b[p], v); v1 = fma(-lv[p + 1], W.b[p + 1], v1); }
-        } else {
-          int p = 0;
-          for (; p + 1 < np; p += 2) {
-            v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
-            v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
+            for (int p = 0; p < 12; p += 2) { v = fma(-lv[p], W.b[p], v); v1 = fma(-lv[p + 1], W.b[p + 1], v1); }
+          } else {
+            int p = 0;
+            for (; p + 1 < np; p += 2) {
+              v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+              v1 = fma(-W.Lp[size_t(p + 1) * N + j], W.b[p + 1], v1);
+            }
+            if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
           }
-          if (p < np) v = fma(-W.Lp[size_t(p) * N + j], W.b[p], v);
+          v += v1;
         }
-        v += v1;
+        vq[q] = v;
       }
       __syncthreads();
-      if (j < N) bx[j] = v;
+#pragma unroll
+      for (int q = 0; q < kPass; ++q) {
+        const int j = tid < Tb ? base0 + q * Tb + tid : N;
+        if (j < N) bx[j] = vq[q];
+      }
     }
   }
   __syncthreads();

@@ -58,6 +58,9 @@ enum ArrayId {
 // dx, dy (read at termination checks only) in the global slab
 __host__ __device__ constexpr bool multi_in_smem(int id) { return id <= AR_IDX || id == AR_PVAL || id == AR_D || id == AR_E; }
 __host__ __device__ constexpr bool big_in_smem(int id) { return id <= AR_IDX; }
+// latency plan: everything in shared memory except the block staging buffers (not needed) and dx, which only the
+// termination checks touch -- with it the H = 20 quadrotor is 1.7 KB over the 227 KB of an SM
+__host__ __device__ constexpr bool smem_in_smem(int id) { return id != AR_STAGE && id != AR_DX; }
 
 constexpr int kMaxRing = 8;   // ring slots per chain
 
@@ -118,7 +121,7 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
 #pragma unroll
   for (int id = 0; id < AR_COUNT; ++id) {
     const size_t sz = (kPlace == PLACE_SMEM && id == AR_STAGE) ? 0 : ((array_doubles(P, id) + 1) & ~size_t(1));
-    const bool in_smem = kPlace == PLACE_SMEM ? true : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (kPlace == PLACE_BIG ? big_in_smem(id) : (smem_mask >> id & 1u) != 0));
+    const bool in_smem = kPlace == PLACE_SMEM ? smem_in_smem(id) || id == AR_STAGE : (kPlace == PLACE_MULTI ? multi_in_smem(id) : (kPlace == PLACE_BIG ? big_in_smem(id) : (smem_mask >> id & 1u) != 0));
     if (in_smem) { ptr[id] = sm; sm += sz; }
     else { ptr[id] = gl; gl += sz; }
     if (kCanaryDoubles > 0 && sz > 0) {   // guard doubles at the end of the array's slot
@@ -1349,7 +1352,7 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
   __shared__ unsigned ring_phase[2];
   Work W;
   carve<kPlace>(W, P, smem_mask, reinterpret_cast<double*>(smem_raw),
-                kPlace == PLACE_SMEM ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles);
+                A.slab + size_t(blockIdx.x) * A.slab_doubles);
   W.ring_bar = ring_bar; W.ring_phase = ring_phase;
   // PLACE_BIG: the staging area is split between the two chains of the twisted sweeps; PLACE_MIXED
   // (generic block code, one chain): the whole area is one ring, provided it is in shared memory and
@@ -1388,7 +1391,7 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
     __syncthreads();
     Work W2;
     carve<kPlace>(W2, P, smem_mask, reinterpret_cast<double*>(smem_raw),
-                  kPlace == PLACE_SMEM ? nullptr : A.slab + size_t(blockIdx.x) * A.slab_doubles, true);
+                  A.slab + size_t(blockIdx.x) * A.slab_doubles, true);
   }
 }
 

@@ -22,6 +22,7 @@ size_t plan_array_doubles(const PatternDev& P, int id);
 int plan_array_count();
 bool plan_multi_in_smem(int id);
 bool plan_big_in_smem(int id);
+bool plan_smem_in_smem(int id);   // latency plan (PLACE_SMEM); the rest goes to the slab
 int plan_stage_array();
 void plan_mixed_priority(std::vector<int>& order);
 bool plan_is_factor_array(int id);   // D^-1, L, L_p blocks   // array ids, most deserving of shared memory first

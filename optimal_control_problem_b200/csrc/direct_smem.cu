@@ -40,6 +40,7 @@ size_t plan_array_doubles(const PatternDev& P, int id) { return array_doubles(P,
 int plan_array_count() { return AR_COUNT; }
 bool plan_multi_in_smem(int id) { return multi_in_smem(id); }
 bool plan_big_in_smem(int id) { return big_in_smem(id); }
+bool plan_smem_in_smem(int id) { return smem_in_smem(id); }
 int plan_stage_array() { return AR_STAGE; }
 bool plan_is_factor_array(int id) { return id == AR_DINV || id == AR_LSUB || id == AR_LP; }
 void plan_mixed_priority(std::vector<int>& order) {

@@ -412,7 +412,7 @@ int plan_launch(ocp_b200_solver* s) {
       multi_smem = multi_slab = big_smem = big_slab = all = 0;
       for (int id = 0; id < count; ++id) {
         const size_t sz = (D::plan_array_doubles(P, id) + 1) & ~size_t(1);
-        if (id != stage_id) all += sz;
+        if (D::plan_smem_in_smem(id)) all += sz;
         (D::plan_multi_in_smem(id) ? multi_smem : multi_slab) += sz;
         (D::plan_big_in_smem(id) ? big_smem : big_slab) += sz;
       }
@@ -450,7 +450,7 @@ int plan_launch(ocp_b200_solver* s) {
         const bool force_stream = place == 0 && std::getenv("OCP_B200_FORCE_STREAM") != nullptr;
         for (int id : order) {
           const size_t sz = (place == 1 && id == stage_id) ? 0 : ((D::plan_array_doubles(P, id) + 1) & ~size_t(1));
-          const bool keep_out = force_stream && D::plan_is_factor_array(id);
+          const bool keep_out = (force_stream && D::plan_is_factor_array(id)) || (place == 1 && !D::plan_smem_in_smem(id));
           if (!keep_out && (place == 1 || used + sz <= avail)) { mask |= 1u << id; used += sz; }
           else slab += sz;
         }

@@ -276,6 +276,60 @@ __device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/,
   }
 }
 
+// border rows of a solve, RW rows per warp: y_p[r] = b_p[r] - sum_j L_p[r][j] y[j] for N <= 320 columns.  The order of
+// the sum of a row does not depend on RW, so every launch plan that takes this path gives the same bits.
+template <int RW, bool kSlab>
+__device__ __forceinline__ void border_rows_warp(const double* __restrict__ Lp, const double* __restrict__ y,
+                                                 const double* __restrict__ bp, double* __restrict__ xp, int N, int warp,
+                                                 int lane) {
+  constexpr int U = 10;
+  double lv[RW][U];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const double* rowp = Lp + size_t(warp * RW + r) * N;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = lane + 32 * u;
+      lv[r][u] = j < N ? rowp[j] : 0.0;
+    }
+  }
+  double yv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = lane + 32 * u;
+    yv[u] = j < N ? y[j] : 0.0;
+  }
+  double s[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; u += 2) { s0 = fma(lv[r][u], yv[u], s0); s1 = fma(lv[r][u + 1], yv[u + 1], s1); }
+    s[r] = s0 + s1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RW; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < RW; ++r) xp[warp * RW + r] = bp[warp * RW + r] - s[r];
+  }
+}
+
+__device__ __forceinline__ bool border_rows_by_warp(int np, int N, int nw) {
+  return np == 12 && N <= 320 && (nw == 4 || nw == 6 || nw == 12);
+}
+
+template <bool kSlab>   // kSlab: L_p is known to live in global memory (the compact kernel's slab)
+__device__ __forceinline__ void border_rows_dispatch(const double* Lp, const double* y, const double* bp, double* xp, int N,
+                                                     int warp, int lane, int nw) {
+  if (nw == 4) border_rows_warp<3, kSlab>(Lp, y, bp, xp, N, warp, lane);
+  else if (nw == 6) border_rows_warp<2, kSlab>(Lp, y, bp, xp, N, warp, lane);
+  else border_rows_warp<1, kSlab>(Lp, y, bp, xp, N, warp, lane);
+}
+
 // K x = b in place: b is [p | block 0 | ... | block nb-1]
 template <int BS>
 __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
@@ -310,6 +364,9 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   // border: y_p = b_p - sum_k L_pk y_k  (half a warp per border row, loads issued in batches of 8
   // so that a slab-resident L_p costs one L2 latency per batch), x_p = D_p^-1 y_p
   if (np > 0) {
+    if (border_rows_by_warp(np, N, nw)) {
+      border_rows_dispatch<false>(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
+    } else {
     const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
     for (int r0 = 0; r0 < np; r0 += nhw) {
       const int r = r0 + hw;
@@ -332,6 +389,7 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (have && hl == 0) W.xp[r] = W.b[r] - s;
+    }
     }
     __syncthreads();
     if (tid < np) {
