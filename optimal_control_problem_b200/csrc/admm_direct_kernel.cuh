@@ -162,8 +162,16 @@ __device__ __forceinline__ void carve(Work& W, const PatternDev& P, uint32_t sme
 struct Rho {
   double ineq, eq, inv_ineq, inv_eq;
   __device__ explicit Rho(double rho) : ineq(rho), eq(kRhoEqOverIneq * rho), inv_ineq(1.0 / rho), inv_eq(1.0 / (kRhoEqOverIneq * rho)) {}
-  __device__ __forceinline__ double of(signed char ct) const { return ct == 1 ? eq : (ct == -1 ? kRhoMin : ineq); }
-  __device__ __forceinline__ double inv(signed char ct) const { return ct == 1 ? inv_eq : (ct == -1 ? 1.0 / kRhoMin : inv_ineq); }
+  // ct == 1 ? a : (ct == -1 ? c : b) as two selects: written as a ternary the compiler rematerialises the equality
+  // value inside a branch region per matrix entry / row (K assembly, update phase)
+  __device__ static __forceinline__ double pick(double a, double b, double c, int ct) {
+    double r;
+    asm("{\n .reg .pred p, q;\n setp.eq.s32 p, %4, 1;\n setp.eq.s32 q, %4, -1;\n selp.f64 %0, %1, %2, p;\n selp.f64 %0, %3, %0, q;\n}"
+        : "=&d"(r) : "d"(a), "d"(b), "d"(c), "r"(ct));
+    return r;
+  }
+  __device__ __forceinline__ double of(signed char ct) const { return pick(eq, ineq, kRhoMin, ct); }
+  __device__ __forceinline__ double inv(signed char ct) const { return pick(inv_eq, inv_ineq, 1.0 / kRhoMin, ct); }
 };
 
 // ---------------------------------------------------------------------------------------

@@ -289,15 +289,18 @@ __device__ __forceinline__ void border_rows_warp(const double* __restrict__ Lp, 
     const double* rowp = Lp + size_t(warp * RW + r) * N;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      // (clamped index + select: a conditional load costs a branch region per element)
       const int j = lane + 32 * u;
-      lv[r][u] = j < N ? rowp[j] : 0.0;
+      const double v = rowp[j < N ? j : N - 1];
+      lv[r][u] = j < N ? v : 0.0;
     }
   }
   double yv[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int j = lane + 32 * u;
-    yv[u] = j < N ? y[j] : 0.0;
+    const double v = y[j < N ? j : N - 1];
+    yv[u] = j < N ? v : 0.0;
   }
   double s[RW];
 #pragma unroll
