@@ -531,6 +531,16 @@ def test_compact_plan_matches_oracle(native, monkeypatch, name, horizon):
         assert st[:, native.STAT["rho_updates"]].sum() >= 1      # the refactorisation path ran
 
 
+def test_launch_plans_of_the_headline_shape(problems, native):
+    """The H = 20 quadrotor runs its small batches on the all-shared-memory placement (it is within 2 KB of the limit:
+    once it did not fit, the plan fell back to the streamed placement and every latency number was 40 % worse without
+    any test noticing) and its large batches on the compact kernel at four CTAs per SM."""
+    prob, _ = problems("quadrotor")
+    plan = prob.solver.launch_plan()
+    assert plan["deep"]["place"] == 1 and plan["deep"]["threads"] == 384
+    assert plan["wide"]["place"] == 4 and plan["wide"]["ctas_per_sm"] == 4
+
+
 def test_compact_plan_qp_level(native, monkeypatch):
     """QP-level entry points on the compact kernel: primal / dual solutions, residuals, the check trace, an
     infeasible QP (certificate -> NaN solution) and inconsistent bounds (zero step)."""
