@@ -306,7 +306,7 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
     if (direct::border_rows_by_warp(np, N, nw)) {
       // whole warps per border row (3 or 2 rows each), every slab load of a warp issued before its first FMA:
       // one L2 round trip for the phase instead of one per 128-column chunk and row pass
-      direct::border_rows_dispatch<true>(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
+      direct::border_rows_dispatch(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
     } else {
     const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
     for (int r0 = 0; r0 < np; r0 += nhw) {
@@ -333,16 +333,7 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
     }
     }
     __syncthreads();
-    if (tid < np) {
-      double s0 = 0.0, s1 = 0.0;
-      int c = 0;
-      for (; c + 1 < np; c += 2) {
-        s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
-        s1 = fma(W.Dp[tid * (np + 1) + c + 1], W.xp[c + 1], s1);
-      }
-      if (c < np) s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
-      W.b[tid] = s0 + s1;
-    }
+    direct::border_apply_inverse(W.Dp, W.xp, W.b, np, tid);
     __syncthreads();
   }
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);

@@ -73,14 +73,21 @@ __device__ __forceinline__ void warp_invert_exact(double* M, int /*ld*/, int lan
 #pragma unroll
   for (int r = 0; r < BS; ++r) col[r] = M[r * ld + cc];
   const double2* piv2 = reinterpret_cast<const double2*>(piv);
+  // 1 / M[k][k] of the NEXT pivot is started by its owner (lane k + 1) as soon as this pivot's multiplier is known:
+  // M[k+1][k+1] <- fma(f[k+1], M[k][k+1], M[k+1][k+1]) is the very update the loop below applies to that element, so
+  // the bits are the same, but the reciprocal (~80 cycles) now overlaps the all-gather round trip and the FMAs
+  // instead of heading the next pivot's dependency chain
+  double rnext = 1.0 / col[0];   // lane 0: 1 / M[0][0]
 #pragma unroll
   for (int k = 0; k < BS; ++k) {
     const double ck = col[k];                                   // M[k][c] == M[c][k]
-    const double ipiv = 1.0 / __shfl_sync(0xffffffffu, ck, k);  // every lane: 1 / M[k][k]
+    const double ipiv = __shfl_sync(0xffffffffu, rnext, k);     // every lane: 1 / M[k][k]
     const bool mine = lane == k;
     // f[lane] = -M[lane][k] / M[k][k].  Rows already pivoted hold the sign-flipped coupling
     // (M[r][k] == -M[k][r] for r < k in in-place Gauss-Jordan), rows still to come are symmetric.
-    if (act) piv[lane] = mine ? ipiv : (lane < k ? ck * ipiv : -ck * ipiv);
+    const double fl = mine ? ipiv : (lane < k ? ck * ipiv : -ck * ipiv);
+    if (act) piv[lane] = fl;
+    if (k + 1 < BS) rnext = 1.0 / fma(fl, ck, col[k + 1 < BS ? k + 1 : k]);   // meaningful on lane k + 1 only
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < BS / 2; ++r) {

@@ -278,7 +278,7 @@ __device__ __forceinline__ void run_chain(const Work& W, double* bx, int /*ld*/,
 
 // border rows of a solve, RW rows per warp: y_p[r] = b_p[r] - sum_j L_p[r][j] y[j] for N <= 320 columns.  The order of
 // the sum of a row does not depend on RW, so every launch plan that takes this path gives the same bits.
-template <int RW, bool kSlab>
+template <int RW, bool kExact>   // kExact: N == 320, no index clamps
 __device__ __forceinline__ void border_rows_warp(const double* __restrict__ Lp, const double* __restrict__ y,
                                                  const double* __restrict__ bp, double* __restrict__ xp, int N, int warp,
                                                  int lane) {
@@ -291,16 +291,16 @@ __device__ __forceinline__ void border_rows_warp(const double* __restrict__ Lp, 
     for (int u = 0; u < U; ++u) {
       // (clamped index + select: a conditional load costs a branch region per element)
       const int j = lane + 32 * u;
-      const double v = rowp[j < N ? j : N - 1];
-      lv[r][u] = j < N ? v : 0.0;
+      const double v = rowp[kExact || j < N ? j : N - 1];
+      lv[r][u] = kExact || j < N ? v : 0.0;
     }
   }
   double yv[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int j = lane + 32 * u;
-    const double v = y[j < N ? j : N - 1];
-    yv[u] = j < N ? v : 0.0;
+    const double v = y[kExact || j < N ? j : N - 1];
+    yv[u] = kExact || j < N ? v : 0.0;
   }
   double s[RW];
 #pragma unroll
@@ -325,12 +325,40 @@ __device__ __forceinline__ bool border_rows_by_warp(int np, int N, int nw) {
   return np == 12 && N <= 320 && (nw == 4 || nw == 6 || nw == 12);
 }
 
-template <bool kSlab>   // kSlab: L_p is known to live in global memory (the compact kernel's slab)
+template <bool kExact>
+__device__ __forceinline__ void border_rows_pick(const double* Lp, const double* y, const double* bp, double* xp, int N,
+                                                 int warp, int lane, int nw) {
+  if (nw == 4) border_rows_warp<3, kExact>(Lp, y, bp, xp, N, warp, lane);
+  else if (nw == 6) border_rows_warp<2, kExact>(Lp, y, bp, xp, N, warp, lane);
+  else border_rows_warp<1, kExact>(Lp, y, bp, xp, N, warp, lane);
+}
 __device__ __forceinline__ void border_rows_dispatch(const double* Lp, const double* y, const double* bp, double* xp, int N,
                                                      int warp, int lane, int nw) {
-  if (nw == 4) border_rows_warp<3, kSlab>(Lp, y, bp, xp, N, warp, lane);
-  else if (nw == 6) border_rows_warp<2, kSlab>(Lp, y, bp, xp, N, warp, lane);
-  else border_rows_warp<1, kSlab>(Lp, y, bp, xp, N, warp, lane);
+  if (N == 320) border_rows_pick<true>(Lp, y, bp, xp, N, warp, lane, nw);
+  else border_rows_pick<false>(Lp, y, bp, xp, N, warp, lane, nw);
+}
+
+// x_p = D_p^-1 y_p by the first np threads (after the barrier that publishes y_p in xp)
+__device__ __forceinline__ void border_apply_inverse(const double* Dp, const double* xp, double* b, int np, int tid) {
+  if (tid >= np) return;
+  if (np == 12) {   // the border size of a 12-state reference: every load issued before the first FMA
+    double d[12], x[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) { d[c] = Dp[tid * 13 + c]; x[c] = xp[c]; }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 12; c += 2) { s0 = fma(d[c], x[c], s0); s1 = fma(d[c + 1], x[c + 1], s1); }
+    b[tid] = s0 + s1;
+    return;
+  }
+  double s0 = 0.0, s1 = 0.0;
+  int c = 0;
+  for (; c + 1 < np; c += 2) {
+    s0 = fma(Dp[tid * (np + 1) + c], xp[c], s0);
+    s1 = fma(Dp[tid * (np + 1) + c + 1], xp[c + 1], s1);
+  }
+  if (c < np) s0 = fma(Dp[tid * (np + 1) + c], xp[c], s0);
+  b[tid] = s0 + s1;
 }
 
 // K x = b in place: b is [p | block 0 | ... | block nb-1]
@@ -368,7 +396,7 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   // so that a slab-resident L_p costs one L2 latency per batch), x_p = D_p^-1 y_p
   if (np > 0) {
     if (border_rows_by_warp(np, N, nw)) {
-      border_rows_dispatch<false>(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
+      border_rows_dispatch(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
     } else {
     const int hw = tid >> 4, hl = tid & 15, nhw = T >> 4;
     for (int r0 = 0; r0 < np; r0 += nhw) {
@@ -395,16 +423,7 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
     }
     }
     __syncthreads();
-    if (tid < np) {
-      double s0 = 0.0, s1 = 0.0;
-      int c = 0;
-      for (; c + 1 < np; c += 2) {
-        s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
-        s1 = fma(W.Dp[tid * (np + 1) + c + 1], W.xp[c + 1], s1);
-      }
-      if (c < np) s0 = fma(W.Dp[tid * (np + 1) + c], W.xp[c], s0);
-      W.b[tid] = s0 + s1;
-    }
+    border_apply_inverse(W.Dp, W.xp, W.b, np, tid);
     __syncthreads();
   }
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
