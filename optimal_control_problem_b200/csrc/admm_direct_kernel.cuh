@@ -785,7 +785,11 @@ __device__ __noinline__ void tri_solve_stream_twisted(const PatternDev& P, const
   const int np = P.tri_np, nb = P.tri_nb;
   constexpr int bs = kBS, ld = kBS + 2;
   const int N = nb * bs, mid = nb / 2;
-  double* const wb = W.b;
+  // b and the ring are in shared memory on this path (PLACE_BIG): re-derive both pointers from the dynamic
+  // shared-memory symbol, so that the sweeps load with LDS and 32-bit addresses instead of generic loads
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const sm0 = reinterpret_cast<double*>(smem_raw);
+  double* const wb = sm0 + (W.b - sm0);
   double* const bx = wb + np;
   const double* const Lsub = W.Lsub;
   const double* const Dinv = W.Dinv;
@@ -808,26 +812,24 @@ __device__ __noinline__ void tri_solve_stream_twisted(const PatternDev& P, const
   const int rr = act ? row : 0;
   constexpr int kPer = (kBS + 3) / 4;
   uint32_t ph = ring_phase[grp];
-  double* ring = W.stage + grp * R * stride;
+  double* ring = sm0 + (W.stage - sm0) + grp * R * stride;
   unsigned long long* bars = W.ring_bar + grp * kMaxRing;
   const int bar_id = 1 + grp;
   OCP_B200_FINE_CLOCK(clk, W.phase);
 
-  // this group's block sequence: forward chain, (group 0: the two joining blocks,) its share of the
-  // diagonal phase, backward chain
+  // this group's block sequence: forward chain, (group 0: the two joining blocks,) backward chain.  The diagonal
+  // phase is not a chain: all threads read their D_k^-1 rows straight from the slab (below) while the ring
+  // already fills with the first blocks of the backward chain.
   const int n_fwd = grp == 0 ? mid - 1 : nb - 2 - mid;
   const int n_join = grp == 0 ? 2 : 0;
-  const int n_diag = grp == 0 ? mid + 1 : nb - 1 - mid;
   const int n_bwd = grp == 0 ? mid : nb - 1 - mid;
-  const int G = n_fwd + n_join + n_diag + n_bwd;
+  const int G = n_fwd + n_join + n_bwd;
   constexpr size_t blk_doubles = size_t(bs) * ld;
   auto gaddr = [&](int g) -> const double* {
     if (g < n_fwd) return Lsub + size_t(grp == 0 ? 1 + g : nb - 1 - g) * blk_doubles;
     g -= n_fwd;
     if (g < n_join) return Lsub + size_t(mid + g) * blk_doubles;
     g -= n_join;
-    if (g < n_diag) return Dinv + size_t(grp == 0 ? g : mid + 1 + g) * blk_doubles;
-    g -= n_diag;
     return Lsub + size_t(grp == 0 ? mid - g : mid + 1 + g) * blk_doubles;
   };
   if (issuer && lane == 0)
@@ -941,43 +943,39 @@ __device__ __noinline__ void tri_solve_stream_twisted(const PatternDev& P, const
   }
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
 
-  // diagonal phase, split between the groups: c_k = D_k^-1 y_k - L_pk' x_p
-  if (in_grp) {
-    const int k0 = grp == 0 ? 0 : mid + 1;
-    constexpr int kMaxLp = 4;   // border rows per lane: np <= 16, else read in place
-    const bool lp_regs = np <= 4 * kMaxLp;
-    double lpn[kMaxLp] = {0.0, 0.0, 0.0, 0.0}, xpv[kMaxLp];
-    auto fetch_lp = [&](int k) {
-#pragma unroll
-      for (int i = 0; i < kMaxLp; ++i) {
-        const int p = sub + 4 * i;
-        lpn[i] = (act && p < np) ? Lp[size_t(p) * N + k * bs + row] : 0.0;
-      }
-    };
-#pragma unroll
-    for (int i = 0; i < kMaxLp; ++i) xpv[i] = (lp_regs && sub + 4 * i < np) ? wb[sub + 4 * i] : 0.0;
-    if (lp_regs && n_diag > 0) fetch_lp(k0);
-    for (int j = 0; j < n_diag; ++j) {
-      const int k = k0 + j;
-      double corr = 0.0;
-      if (lp_regs) {
-#pragma unroll
-        for (int i = 0; i < kMaxLp; ++i) corr = fma(lpn[i], xpv[i], corr);
-        if (j + 1 < n_diag) fetch_lp(k + 1);
-      } else if (act) {
-        for (int p = sub; p < np; p += 4) corr = fma(Lp[size_t(p) * N + k * bs + row], wb[p], corr);
-      }
+  // diagonal phase: c_k = D_k^-1 y_k - L_pk' x_p, one row per thread and pass, whole blocks per pass (a pass never
+  // reads what it overwrites); every load of a row is issued before its first FMA (one L2 round trip per pass
+  // instead of one ring stage per block: 50 dependent stages -> 3 passes for the H = 200 cart-pole)
+  {
+    const int Tb = (T / bs) * bs;
+    for (int base = 0; base < N; base += Tb) {
+      const int j = tid < Tb ? base + tid : N;
       double v = 0.0;
-      if (part) {
-        ring_wait(bars + s, (ph >> s) & 1u);
-        ph ^= 1u << s;
-        v = block_dot(ring + s * stride, bx + k * bs, false);
-        corr += __shfl_xor_sync(0xffffffffu, corr, 1);
-        corr += __shfl_xor_sync(0xffffffffu, corr, 2);
+      if (j < N) {
+        const int k = j / bs, r = j - k * bs;
+        const double2* d2 = reinterpret_cast<const double2*>(Dinv + size_t(k) * blk_doubles + r * ld);
+        const double* yk = bx + k * bs;
+        double dr[bs];
+#pragma unroll
+        for (int t = 0; t < bs / 2; ++t) { const double2 x = d2[t]; dr[2 * t] = x.x; dr[2 * t + 1] = x.y; }
+        double corr = 0.0, corr1 = 0.0;
+        if (np == 4) {
+          double l0 = Lp[j], l1 = Lp[size_t(N) + j], l2 = Lp[2 * size_t(N) + j], l3 = Lp[3 * size_t(N) + j];
+          corr = fma(l0, wb[0], fma(l2, wb[2], 0.0));
+          corr1 = fma(l1, wb[1], fma(l3, wb[3], 0.0));
+        } else {
+          for (int p = 0; p < np; ++p) corr = fma(Lp[size_t(p) * N + j], wb[p], corr);
+        }
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int t = 0; t < bs; t += 4) {
+          s0 = fma(dr[t], yk[t], s0); s1 = fma(dr[t + 1], yk[t + 1], s1);
+          s2 = fma(dr[t + 2], yk[t + 2], s2); s3 = fma(dr[t + 3], yk[t + 3], s3);
+        }
+        v = ((s0 + s1) + (s2 + s3)) - (corr + corr1);
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nbar) : "memory");   // every row has read y_k
-      if (act && sub == 0) bx[k * bs + row] = v - corr;
-      advance();
+      __syncthreads();
+      if (j < N) bx[j] = v;
     }
   }
   __syncthreads();
