@@ -544,7 +544,12 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   const int bs = kBS > 0 ? kBS : P.tri_bs, ld = kBS > 0 ? kBS + 2 : P.tri_ld, N = nb * bs;
   // fields are copied into locals: W and P live in the caller's frame and the "memory" clobbers of the
   // barrier / bulk-copy instructions would turn each later use into a reload through local memory
-  double* const wb = W.b;
+  // b and the ring slots are in shared memory whenever this function runs (the kernel checks the placement mask
+  // before it sets ring_slots): both pointers are re-derived from the dynamic shared-memory symbol, so that the
+  // sweeps load with LDS and 32-bit addresses instead of generic loads
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const sm0 = reinterpret_cast<double*>(smem_raw);
+  double* const wb = sm0 + (W.b - sm0);
   double* const bx = wb + np;
   const double* const Lsub = W.Lsub;
   const double* const Dinv = W.Dinv;
@@ -552,8 +557,8 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   double* const xp = W.xp;
   const double* const Dp = W.Dp;
   double* const Dp2 = W.Dp2;
-  double* const stage = W.stage;
-  double* const Sbuf = W.S;
+  double* const stage = sm0 + (W.stage - sm0);
+  double* const Sbuf = sm0 + (W.S - sm0);   // (a ring slot only when the scratch is in shared memory too)
   unsigned long long* const ring_bar = W.ring_bar;
   unsigned* const ring_phase = W.ring_phase;
   const int s_stride = W.s_stride, stage_slots = P.stage_slots;
@@ -577,13 +582,18 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   // The three block phases form ONE stream of G = 2 (nb - 1) + nb blocks, so the ring never drains
   // between them (and keeps filling during the border phase): stream position g -> block address.
   // Ring slots: the staging area, then the two block-sized scratch buffers of the factorisation.
-  const int G = 2 * (nb - 1) + nb;
+  // (compile-time block size: the diagonal phase is not part of the stream -- all threads read their D_k^-1 rows
+  // straight from the slab, see below -- and the ring goes from the forward blocks to the backward blocks)
+  constexpr bool kParallelDiag = kBS > 0;
+  const int G = 2 * (nb - 1) + (kParallelDiag ? 0 : nb);
   const size_t blk_doubles = size_t(bs) * ld;
   auto gaddr = [&](int g) -> const double* {
     if (g < nb - 1) return Lsub + size_t(1 + g) * blk_doubles;
     g -= nb - 1;
-    if (g < nb) return Dinv + size_t(g) * blk_doubles;
-    g -= nb;
+    if (!kParallelDiag) {
+      if (g < nb) return Dinv + size_t(g) * blk_doubles;
+      g -= nb;
+    }
     return Lsub + size_t(nb - 1 - g) * blk_doubles;
   };
   auto slot_ptr = [&](int sl) -> double* {
@@ -705,9 +715,60 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   }
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BORDER);
 
-  // diagonal phase: c_k = D_k^-1 y_k - L_pk' x_p, block by block through the ring; the L_p values of
-  // the next block are requested before the current block is multiplied
-  if (in_loop) {
+  // diagonal phase: c_k = D_k^-1 y_k - L_pk' x_p.  Compile-time block size: one row per thread and pass, whole
+  // blocks per pass (a pass never reads what it overwrites), every load of a row issued before its first FMA --
+  // the phase runs at the rate the slab delivers D^-1 and L_p to ALL threads instead of one ring stage per block.
+  // Any block size: block by block through the ring; the L_p values of the next block are requested before the
+  // current block is multiplied.
+  if constexpr (kParallelDiag) {
+    // four lanes per row (9 of 36 columns each: few enough registers that every load of a pass is in flight
+    // before the first FMA -- this kernel runs 768 threads at 80 registers), T / 4 rows per pass, whole blocks
+    static_assert(kBS % 4 == 0, "columns split over four lanes");
+    constexpr int kPerD = kBS / 4, kMaxLp = 8;   // border rows per lane: np <= 32, else a loop
+    const int rows_pass = ((T >> 2) / kBS) * kBS;
+    const int prow = tid >> 2, psub = tid & 3;
+    for (int base = 0; base < N; base += rows_pass) {
+      const int j = prow < rows_pass ? base + prow : N;
+      const bool have = j < N;
+      const int jj = have ? j : 0;   // (clamped: unconditional loads, result dropped)
+      const int k = jj / kBS, r = jj - k * kBS;
+      const double* drow = Dinv + size_t(k) * blk_doubles + r * ld + psub;
+      const double* yk = bx + k * kBS + psub;
+      double mv[kPerD], sv[kPerD], lv[kMaxLp], xv[kMaxLp];
+#pragma unroll
+      for (int i = 0; i < kPerD; ++i) mv[i] = drow[4 * i];
+#pragma unroll
+      for (int i = 0; i < kMaxLp; ++i) {
+        const int pp = psub + 4 * i;
+        lv[i] = Lp[size_t(pp < np ? pp : 0) * N + jj];
+      }
+#pragma unroll
+      for (int i = 0; i < kPerD; ++i) sv[i] = yk[4 * i];
+#pragma unroll
+      for (int i = 0; i < kMaxLp; ++i) {
+        const int pp = psub + 4 * i;
+        const double x = wb[pp < np ? pp : 0];
+        xv[i] = pp < np ? x : 0.0;
+      }
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < kPerD; i += 3) {
+        s0 = fma(mv[i], sv[i], s0);
+        if (i + 1 < kPerD) s1 = fma(mv[i + 1], sv[i + 1], s1);
+        if (i + 2 < kPerD) s2 = fma(mv[i + 2], sv[i + 2], s2);
+      }
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < kMaxLp; i += 2) { c0 = fma(lv[i], xv[i], c0); c1 = fma(lv[i + 1], xv[i + 1], c1); }
+      double v = ((s0 + s1) + s2) - (c0 + c1);
+      if (np > 4 * kMaxLp)
+        for (int pp = psub + 4 * kMaxLp; pp < np; pp += 4) v = fma(-Lp[size_t(pp) * N + jj], wb[pp], v);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      __syncthreads();
+      if (have && psub == 0) bx[j] = v;
+    }
+  } else if (in_loop) {
     const int count = nb;
     constexpr int kMaxLp = 8;   // border rows per lane: np <= 32
     const bool lp_regs = np <= 4 * kMaxLp;
@@ -1364,8 +1425,8 @@ admm_direct_kernel(const PatternDev P, const ocp_b200_settings S, const SolveArg
   // (generic block code, one chain): the whole area is one ring, provided it is in shared memory and
   // the factor is not
   W.ring_slots = (kPlace == PLACE_BIG && P.stage_slots >= 6) ? min(P.stage_slots / 2, kMaxRing) : 0;
-  if (kPlace == PLACE_MIXED && !exact_block_code(P) && (smem_mask >> AR_STAGE & 1u) && !(smem_mask >> AR_LSUB & 1u) &&
-      !(smem_mask >> AR_DINV & 1u))
+  if (kPlace == PLACE_MIXED && !exact_block_code(P) && (smem_mask >> AR_STAGE & 1u) && (smem_mask >> AR_B & 1u) &&
+      !(smem_mask >> AR_LSUB & 1u) && !(smem_mask >> AR_DINV & 1u))
     W.ring_slots = min((P.stage_slots > 0 ? P.stage_slots : 4) + ((smem_mask >> AR_SCRATCH & 1u) ? 2 : 0), kMaxRing);
   if ((kPlace == PLACE_BIG || kPlace == PLACE_MIXED) && threadIdx.x == 0) {
     for (int i = 0; i < 2 * kMaxRing; ++i)
