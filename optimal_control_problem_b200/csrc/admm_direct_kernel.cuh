@@ -584,7 +584,10 @@ __device__ inline void tri_solve_stream(const PatternDev& P, const Work& W) {
   // Ring slots: the staging area, then the two block-sized scratch buffers of the factorisation.
   // (compile-time block size: the diagonal phase is not part of the stream -- all threads read their D_k^-1 rows
   // straight from the slab, see below -- and the ring goes from the forward blocks to the backward blocks)
-  constexpr bool kParallelDiag = kBS > 0;
+#ifndef OCP_B200_RING_DIAG
+#define OCP_B200_RING_DIAG 0   // 1: the diagonal phase through the ring as well (A/B measurements)
+#endif
+  constexpr bool kParallelDiag = kBS > 0 && !OCP_B200_RING_DIAG;
   const int G = 2 * (nb - 1) + (kParallelDiag ? 0 : nb);
   const size_t blk_doubles = size_t(bs) * ld;
   auto gaddr = [&](int g) -> const double* {
