@@ -927,16 +927,27 @@ __device__ __noinline__ void tri_solve_stream_twisted(const PatternDev& P, const
     return sum;
   };
   // one sweep stage: dst block -= M src block (M row-wise in the forward sweeps, transposed in the backward ones)
+#ifdef OCP_B200_SWEEP_PROBE   // stage anatomy (thread 0): wait for the block / product / barrier / next issue
+  PhaseClock pclk(W.phase);
+#define OCP_B200_PROBE_LAP(slot) pclk.lap(slot)
+#else
+#define OCP_B200_PROBE_LAP(slot)
+#endif
   auto sweep = [&](int dstb, int srcb, bool column) {
+    OCP_B200_PROBE_LAP(OCP_B200_PHASE_SOLVE_BWD);
     if (part) {
       ring_wait(bars + s, (ph >> s) & 1u);
       ph ^= 1u << s;
+      OCP_B200_PROBE_LAP(OCP_B200_PHASE_FACTOR_INVERT);
       const double old = (act && sub == 0) ? bx[dstb * bs + row] : 0.0;
       const double sum = block_dot(ring + s * stride, bx + srcb * bs, column);
       if (act && sub == 0) bx[dstb * bs + row] = old - sum;
+      OCP_B200_PROBE_LAP(OCP_B200_PHASE_FACTOR_STEP);
     }
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nbar) : "memory");
+    OCP_B200_PROBE_LAP(OCP_B200_PHASE_SOLVE_DIAG);
     advance();
+    OCP_B200_PROBE_LAP(OCP_B200_PHASE_SOLVE_BORDER);
   };
 
   // forward: top chain y_k = b_k - L_k y_{k-1} (k = 1..mid-1), bottom chain y_k = b_k - U_k y_{k+1} (k = nb-2..mid+1)

@@ -264,6 +264,25 @@ ModelSource generate(const ModelSpec& spec) {
       for (size_t j = 0; j < seeds->size(); ++j) em.leaf[(*seeds)[j].id()] = "S" + std::to_string(j);
   };
 
+  // lanes per (instance, group) unit: a group has at most `maxcols` tangent directions, so a warp of 32 lanes
+  // carries 32 / L units of the SAME group (consecutive instances: same template, no divergence).  The H = 20
+  // quadrotor has 16-column groups: one unit per warp leaves half the lanes idle.
+  int maxcols = 1;
+  for (const GroupPlan& gp : groups) maxcols = std::max(maxcols, gp.ncols);
+  int max_image = 1;   // doubles of the largest per-unit shared-memory image (A range + H range of a group)
+  {
+    int ma = 0, mh = 0;
+    for (const GroupPlan& gp : groups) { ma = std::max(ma, gp.a_len); mh = std::max(mh, gp.h_len); }
+    max_image = std::max(1, ma + mh);
+  }
+  int L = 32;
+  // (4 warps per block, static shared memory: keep the images of a block under 40 KB)
+  while (L > 8 && L / 2 >= maxcols && size_t(4) * (32 / (L / 2)) * max_image * sizeof(double) <= 40 * 1024) L /= 2;
+  if (const char* e = std::getenv("OCP_B200_ASSEMBLE_LANES")) {
+    const int v = std::atoi(e);
+    if (v == 8 || v == 16 || v == 32) L = std::max(v, L);   // only wider than needed (diagnostics)
+  }
+
   for (int gidx = 0; gidx < G; ++gidx) {
     GroupPlan& g = groups[gidx];
     stage_a = std::max(stage_a, g.a_len);
@@ -315,23 +334,23 @@ ModelSource generate(const ModelSpec& spec) {
     for (const SXElem& e : cvals) em.require(e);
     for (const SXElem& e : qvals) em.require(e);
     for (const SXElem& e : tang) em.require(e);
-    // lane-select stores of the primal outputs: output i lives on lane i % 32
+    // lane-select stores of the primal outputs: output i lives on lane i % L of the unit
     auto lane_select = [&](const std::vector<SXElem>& vals, const char* var, int chunk) {
       std::ostringstream s;
       s << "    double " << var << " = 0.0;\n";
-      for (int i = chunk * 32; i < std::min<int>(vals.size(), chunk * 32 + 32); ++i)
-        s << "    if (lane == " << (i % 32) << ") " << var << " = " << em.ref(vals[i]) << ";\n";
+      for (int i = chunk * L; i < std::min<int>(vals.size(), chunk * L + L); ++i)
+        s << "    if (lane == " << (i % L) << ") " << var << " = " << em.ref(vals[i]) << ";\n";
       return s.str();
     };
-    for (int c = 0; c * 32 < static_cast<int>(cvals.size()); ++c) {
+    for (int c = 0; c * L < static_cast<int>(cvals.size()); ++c) {
       stores << "  {\n" << lane_select(cvals, "cv", c);
-      stores << "    const int i = " << c * 32 << " + lane;\n";
+      stores << "    const int i = " << c * L << " + lane;\n";
       stores << "    if (first_pass && i < " << cvals.size() << ") { const int r = ctab[i]; "
              << "l[r] = lbg[r - NVAR] - cv; u[r] = ubg[r - NVAR] - cv; }\n  }\n";
     }
-    for (int c = 0; c * 32 < static_cast<int>(qvals.size()); ++c) {
+    for (int c = 0; c * L < static_cast<int>(qvals.size()); ++c) {
       stores << "  {\n" << lane_select(qvals, "qv", c);
-      stores << "    const int i = " << c * 32 << " + lane;\n";
+      stores << "    const int i = " << c * L << " + lane;\n";
       stores << "    if (first_pass && i < " << qvals.size() << ") q[firstcol + i] = qv;\n  }\n";
     }
     for (int k = 0; k < g.n_tg; ++k)
@@ -388,7 +407,8 @@ ModelSource generate(const ModelSpec& spec) {
   // resident blocks per SM the assembly kernel is compiled for (register cap = 65536 / (128 * blocks))
   int min_blocks = 4;   // measured on B200 (quadrotor, B=4096): 1.20 ms at 2, 0.94 at 3, 0.89 at 4
   if (const char* e = std::getenv("OCP_B200_ASSEMBLE_MIN_BLOCKS")) min_blocks = std::max(1, std::atoi(e));
-  s << "constexpr int WARPS_PER_BLOCK = 4, MIN_BLOCKS = " << min_blocks << ";\n\n";
+  s << "constexpr int WARPS_PER_BLOCK = 4, MIN_BLOCKS = " << min_blocks << ";\n";
+  s << "constexpr int UNIT_LANES = " << L << ", UNITS_PER_WARP = 32 / UNIT_LANES;   // lanes per (instance, group) unit\n\n";
   s << "struct GroupInfo { int tmpl, otmpl, first_col, ncols, xoff, a_base, a_len, h_base, h_len, atab_off, "
        "htab_off, ctab_off; };\n";
   s << "__constant__ GroupInfo c_groups[NUM_GROUPS] = {\n";
@@ -407,13 +427,14 @@ ModelSource generate(const ModelSpec& spec) {
 __device__ __forceinline__ double ocp_sign(double a) { return a > 0.0 ? 1.0 : (a < 0.0 ? -1.0 : 0.0); }
 
 // shared -> global copy of one contiguous value range, 16-byte stores where aligned
+// (by the UNIT_LANES lanes of one unit; lane = lane within the unit)
 __device__ __forceinline__ void copy_out(double* __restrict__ dst, const double* __restrict__ src, int len, int lane) {
   int head = ((reinterpret_cast<unsigned long long>(dst) & 15ULL) != 0ULL && len > 0) ? 1 : 0;
   if (head && lane == 0) dst[0] = src[0];
   const int pairs = (len - head) >> 1;
   double2* d2 = reinterpret_cast<double2*>(dst + head);
-  for (int i = lane; i < pairs; i += 32) d2[i] = make_double2(src[head + 2 * i], src[head + 2 * i + 1]);
-  if (((len - head) & 1) && lane == 31) dst[len - 1] = src[len - 1];
+  for (int i = lane; i < pairs; i += UNIT_LANES) d2[i] = make_double2(src[head + 2 * i], src[head + 2 * i + 1]);
+  if (((len - head) & 1) && lane == UNIT_LANES - 1) dst[len - 1] = src[len - 1];
 }
 
 )";
@@ -430,20 +451,25 @@ __device__ __forceinline__ void copy_out(double* __restrict__ dst, const double*
       << "(const double* __restrict__ X, const double* __restrict__ P) {\n" << otmpl_text[t] << "}\n\n";
   }
   s << R"(
-// one warp per (instance, column group)
+// one warp per column group and UNITS_PER_WARP consecutive instances (UNIT_LANES lanes each)
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS)
 assemble_kernel(const int B, const double* __restrict__ x, const double* __restrict__ p,
                 const double* __restrict__ frames, const double* __restrict__ lbx, const double* __restrict__ ubx,
                 const double* __restrict__ lbg, const double* __restrict__ ubg, double* __restrict__ hv, const int ldh,
                 double* __restrict__ q, const int ldn, double* __restrict__ av, const int lda,
                 double* __restrict__ l, double* __restrict__ u, const int ldm) {
-  __shared__ double smem[WARPS_PER_BLOCK * (STAGE_A + STAGE_H)];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  __shared__ double smem[WARPS_PER_BLOCK * UNITS_PER_WARP * (STAGE_A + STAGE_H)];
+  const int wlane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int lane = wlane % UNIT_LANES, unit = wlane / UNIT_LANES;   // lane within the unit
   const long long gw = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + wib;
-  if (gw >= static_cast<long long>(B) * NUM_GROUPS) return;
-  const int inst = static_cast<int>(gw / NUM_GROUPS), grp = static_cast<int>(gw % NUM_GROUPS);
+  const long long ngroups_inst = (static_cast<long long>(B) + UNITS_PER_WARP - 1) / UNITS_PER_WARP;
+  if (gw >= ngroups_inst * NUM_GROUPS) return;
+  const int grp = static_cast<int>(gw % NUM_GROUPS);
+  const int inst_raw = static_cast<int>(gw / NUM_GROUPS) * UNITS_PER_WARP + unit;
+  const bool valid = inst_raw < B;            // (a ragged last warp: its idle units run the code, store nothing)
+  const int inst = valid ? inst_raw : B - 1;
   const GroupInfo gi = c_groups[grp];
-  double* sA = smem + wib * (STAGE_A + STAGE_H);
+  double* sA = smem + (wib * UNITS_PER_WARP + unit) * (STAGE_A + STAGE_H);
   double* sH = sA + STAGE_A;
   const double* xi = x + static_cast<size_t>(inst) * NX;
   const double* pi = p + static_cast<size_t>(inst) * NP;
@@ -451,7 +477,7 @@ assemble_kernel(const int B, const double* __restrict__ x, const double* __restr
   double* ui = u + static_cast<size_t>(inst) * ldm;
   double* qi = q + static_cast<size_t>(inst) * ldn;
   // identity rows of c = [p; x; g]: A entry 1, bounds l - w, u - w (first frame pinned to `frames`)
-  for (int j = lane; j < gi.ncols; j += 32) {
+  for (int j = lane; valid && j < gi.ncols; j += UNIT_LANES) {
     const int col = gi.first_col + j;
     sA[d_acol[col] - gi.a_base] = 1.0;
     double c, lo, hi;
@@ -466,21 +492,23 @@ assemble_kernel(const int B, const double* __restrict__ x, const double* __restr
     li[col] = lo - c;
     ui[col] = hi - c;
   }
-  const int npass = (gi.ncols + 31) >> 5;
+  const int npass = (gi.ncols + UNIT_LANES - 1) / UNIT_LANES;
   for (int pass = 0; pass < npass; ++pass) {
-    const int dir = pass * 32 + lane;
+    const int dir = valid ? pass * UNIT_LANES + lane : (1 << 20);   // no direction: no tangent stores
     switch (gi.tmpl) {
 )";
   for (size_t t = 0; t < tmpl_text.size(); ++t)
     s << "      case " << t << ": stage_tmpl_" << t
       << "(xi + gi.xoff, pi, dir, lane, gi.first_col, d_tab + gi.atab_off, d_tab + gi.htab_off, d_tab + gi.ctab_off, "
-         "sA, sH, lbg, ubg, li, ui, qi, pass == 0); break;\n";
+         "sA, sH, lbg, ubg, li, ui, qi, valid && pass == 0); break;\n";
   s << R"(      default: break;
     }
   }
   __syncwarp();
-  copy_out(av + static_cast<size_t>(inst) * lda + gi.a_base, sA, gi.a_len, lane);
-  copy_out(hv + static_cast<size_t>(inst) * ldh + gi.h_base, sH, gi.h_len, lane);
+  if (valid) {
+    copy_out(av + static_cast<size_t>(inst) * lda + gi.a_base, sA, gi.a_len, lane);
+    copy_out(hv + static_cast<size_t>(inst) * ldh + gi.h_base, sH, gi.h_len, lane);
+  }
 }
 
 // one warp per instance; lane g sums the objective terms of groups g, g+32, ...
@@ -519,7 +547,7 @@ extern "C" int ocp_b200_model_assemble(int B, const double* x, const double* p, 
                                        double* h_vals, int ld_h, double* q, int ld_n, double* a_vals, int ld_a,
                                        double* l, double* u, int ld_m, void* stream) {
   if (B <= 0) return 0;
-  const long long warps = static_cast<long long>(B) * NUM_GROUPS;
+  const long long warps = ((static_cast<long long>(B) + UNITS_PER_WARP - 1) / UNITS_PER_WARP) * NUM_GROUPS;
   const unsigned blocks = static_cast<unsigned>((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   assemble_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       B, x, p, frames, lbx, ubx, lbg, ubg, h_vals, ld_h, q, ld_n, a_vals, ld_a, l, u, ld_m);
