@@ -544,7 +544,7 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
   clk.lap(OCP_B200_PHASE_SCALE);
   direct::tri_assemble_program(P, W, rv, sigma);
   clk.lap(OCP_B200_PHASE_KKT_ASSEMBLE);
-  direct::tri_factor_twisted<BS>(P, W);   // scratch: the iteration vectors (nothing lives there yet)
+  direct::tri_factor_twisted<BS, true>(P, W);   // scratch: the iteration vectors (nothing lives there yet)
   if constexpr (BS == 16) tmem_publish<BS>(W, P.tri_nb, tmem);
   clk.lap(OCP_B200_PHASE_FACTOR);
   // ---- cold start ----
@@ -747,7 +747,7 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
         // (inlined a second time on purpose: an out-of-line copy shared with the set-up was measured slower,
         // 9.6 -> 9.8 ms per launch with P and W passed by value, 11.7 ms by reference)
         direct::tri_assemble_program(P, W, rv, sigma);
-        direct::tri_factor_twisted<BS>(P, W);
+        direct::tri_factor_twisted<BS, true>(P, W);
         if constexpr (BS == 16) tmem_publish<BS>(W, P.tri_nb, tmem);
         for (int j = tid; j < n; j += T) W.x[j] = X.sx[j];
         for (int i = tid; i < m; i += T) {

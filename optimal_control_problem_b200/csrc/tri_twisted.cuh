@@ -25,7 +25,10 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 //   C  = slot content: K_{s,s-1}; the step owns block k, the previously eliminated neighbour is `pred`
 //   kTop: k = s, pred = s - 1, coupling = C Dinv_pred;  else: k = s - 1, pred = s, coupling = C' Dinv_pred
 // Updates D_k (not inverted here), V_k, finalises L_p,pred, accumulates into Dpacc, overwrites the slot.
-template <int BS, bool kTop>
+// kStaged: the caller guarantees stage != nullptr and F != nullptr (the compact kernel): without the run-time choice
+// between a global and a shared-memory operand the compiler keeps the address space of both and the dot products
+// load with LDS instead of generic loads.
+template <int BS, bool kTop, bool kStaged = false>
 __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*ld*/, int k, int pred, int slot, double* S,
                                            double* Sp, double* Dpacc, int gt, int GT, int bar, double* stage, double* F = nullptr) {
   constexpr int bb = BS * BS, ld = BS + 2;   // compile-time pitch: addresses fold into immediates
@@ -37,7 +40,7 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
   // copy the two blocks this step multiplies into shared memory once (coalesced 16-byte loads).
   const double* C = Cg;
   const double* Dm = Dg;
-  if (stage != nullptr) {
+  if (kStaged || stage != nullptr) {
     double2* cs = reinterpret_cast<double2*>(stage);
     double2* ds = reinterpret_cast<double2*>(stage + W.stage_stride);
     const double2* cg2 = reinterpret_cast<const double2*>(Cg);
@@ -67,13 +70,13 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
     const double f = dot_cc<BS>(Sp + r * BS, Dm + c * ld);
     W.Lp[size_t(r) * N + k * BS + c] -= s;
     W.Lp[size_t(r) * N + pred * BS + c] = f;
-    if (F != nullptr) F[e] = f;   // shared-memory copy of L_p,pred for the accumulation below (L_p may live in the slab)
+    if (kStaged || F != nullptr) F[e] = f;   // shared-memory copy of L_p,pred for the accumulation below (L_p may live in the slab)
   }
   group_barrier(bar, GT);
   // D_p accumulator += V_pred L_p,pred';  slot <- coupling
   for (int e = gt; e < np * np; e += GT) {
     const int r = e / np, c = e - r * np;
-    Dpacc[r * (np + 1) + c] += F != nullptr ? dot_cc<BS>(Sp + r * BS, F + c * BS)
+    Dpacc[r * (np + 1) + c] += (kStaged || F != nullptr) ? dot_cc<BS>(Sp + r * BS, F + c * BS)
                                             : dot_cs<BS>(Sp + r * BS, W.Lp + size_t(c) * N + pred * BS, 1);
   }
   for (int e = gt; e < bb; e += GT) {
@@ -83,7 +86,7 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
   group_barrier(bar, GT);
 }
 
-template <int BS>
+template <int BS, bool kStaged = false>
 __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   const int np = P.tri_np, nb = P.tri_nb, N = nb * BS;
@@ -95,8 +98,8 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   double* Sp = W.Sp + grp * W.sp_stride;
   double* piv = W.piv + grp * 32;
   double* Dpacc = W.Dp2 + grp * np * (np + 1);
-  double* stage = W.stage ? W.stage + grp * 2 * W.stage_stride : nullptr;
-  double* F = W.Fb ? W.Fb + grp * W.sp_stride : nullptr;   // shared-memory copy of the L_p block just finished (optional)
+  double* stage = (kStaged || W.stage) ? W.stage + grp * 2 * W.stage_stride : nullptr;
+  double* F = (kStaged || W.Fb) ? W.Fb + grp * W.sp_stride : nullptr;   // shared-memory copy of the L_p block just finished (optional)
   for (int e = gt; e < np * (np + 1); e += GT) Dpacc[e] = 0.0;
   // both chains: invert the chain's current block, then eliminate into the next one
   if (grp == 0) {
@@ -105,14 +108,14 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(1, GT);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_INVERT);
-      chain_step<BS, true>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage, F);
+      chain_step<BS, true, kStaged>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage, F);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_STEP);
     }
   } else {
     for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(2, GT);
-      chain_step<BS, false>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage, F);
+      chain_step<BS, false, kStaged>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage, F);
     }
     if (mid + 1 < nb) {                       // block mid+1: inverted here, eliminated into mid below
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid + 1) * BS * ld, ld, lane, piv);
@@ -121,7 +124,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   }
   __syncthreads();
   // the bottom chain's last step lands on block mid as well: run it with the whole CTA
-  if (mid + 1 < nb) chain_step<BS, false>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage, W.Fb);
+  if (mid + 1 < nb) chain_step<BS, false, kStaged>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage, W.Fb);
   if (tid < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid) * BS * ld, ld, lane, W.piv);
   __syncthreads();
   // border of the last block, then D_p = K_pp - (accumulated) - V_mid L_p,mid', inverted
@@ -137,14 +140,14 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
       const int r = e / BS, c = e % BS;
       const double f = dot_cc<BS>(W.Sp + r * BS, Dm + c * ld);
       W.Lp[size_t(r) * N + mid * BS + c] = f;
-      if (W.Fb != nullptr) W.Fb[e] = f;
+      if (kStaged || W.Fb != nullptr) W.Fb[e] = f;
     }
     __syncthreads();
     for (int e = tid; e < np * np; e += T) {
       const int r = e / np, c = e - r * np;
       const int o = r * (np + 1) + c;
       W.Dp[o] -= W.Dp2[o] + W.Dp2[np * (np + 1) + o] +
-                 (W.Fb != nullptr ? dot_cc<BS>(W.Sp + r * BS, W.Fb + c * BS)
+                 ((kStaged || W.Fb != nullptr) ? dot_cc<BS>(W.Sp + r * BS, W.Fb + c * BS)
                                   : dot_cs<BS>(W.Sp + r * BS, W.Lp + size_t(c) * N + mid * BS, 1));
     }
     __syncthreads();
