@@ -143,8 +143,15 @@ __device__ __forceinline__ void for_rows_A(const CompactIdx& C, const uint32_t* 
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     const PSpan s = pspan_dev(C.arow, ar, i);
     double acc = 0.0;
+    if (s.qd >= 0 && s.qd2 >= 0) {   // every entry of the row's region moves by the same delta: one 16-bit load + add
+      const double* av = Aval + s.qd2;
+      const double* sv = src + s.qd;
 #pragma unroll 4
-    for (int kt = s.kt0; kt < s.kt1; ++kt) acc += Aval[pvalue(tp[kt], s.q)] * src[pvalue(tc[kt], s.q)];
+      for (int kt = s.kt0; kt < s.kt1; ++kt) acc += av[plow(tp, kt)] * sv[plow(tc, kt)];
+    } else {
+#pragma unroll 4
+      for (int kt = s.kt0; kt < s.kt1; ++kt) acc += Aval[pvalue(tp[kt], s.q)] * src[pvalue(tc[kt], s.q)];
+    }
     f(i, acc);
   }
 }
@@ -482,8 +489,14 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
       for (int i = tid; i < m; i += T) {
         const PSpan s = pspan_dev(C.arow, ar, i);
         double en = 0.0;
+        if (s.qd2 >= 0) {
+          const double* av = W.Aval + s.qd2;
 #pragma unroll 4
-        for (int kt = s.kt0; kt < s.kt1; ++kt) en = fmax(en, fabs(W.Aval[pvalue(tr2[kt], s.q)]));
+          for (int kt = s.kt0; kt < s.kt1; ++kt) en = fmax(en, fabs(av[plow(tr2, kt)]));
+        } else {
+#pragma unroll 4
+          for (int kt = s.kt0; kt < s.kt1; ++kt) en = fmax(en, fabs(W.Aval[pvalue(tr2[kt], s.q)]));
+        }
         rs[i] = 1.0 / sqrt(limit_scaling(en));
       }
       __syncthreads();
@@ -583,8 +596,15 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
         const double lo = W.l[i], hi = W.u[i];   // slab: requested before the row product
         const PSpan s = pspan_dev(C.arow, ar, i);
         double zt = 0.0;
+        if (s.qd >= 0 && s.qd2 >= 0) {   // uniform deltas in the row's region (periodic_index.h)
+          const double* av = W.Aval + s.qd2;
+          const double* bv = W.b + s.qd;
 #pragma unroll 4
-        for (int kt = s.kt0; kt < s.kt1; ++kt) zt += W.Aval[pvalue(tp[kt], s.q)] * W.b[pvalue(tc[kt], s.q)];
+          for (int kt = s.kt0; kt < s.kt1; ++kt) zt += av[plow(tp, kt)] * bv[plow(tc, kt)];
+        } else {
+#pragma unroll 4
+          for (int kt = s.kt0; kt < s.kt1; ++kt) zt += W.Aval[pvalue(tp[kt], s.q)] * W.b[pvalue(tc[kt], s.q)];
+        }
         const signed char ct = W.ctype[i];
         const double rh = rv.of(ct);
         const double zr = relax * zt + (1.0 - relax) * W.z[i];

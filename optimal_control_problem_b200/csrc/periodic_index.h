@@ -43,7 +43,8 @@ struct PRegion {
   int kt0;           // template position of k0
   float inv_period;  // 1 / period
   float inv_dk;      // 1 / dk  (0 when dk == 0)
-  int pad;
+  int uni;           // (d + 1) | (d2 + 1) << 16 when every entry of the region moves by the same delta d (first
+                     // payload) / d2 (second payload) per repetition, 0 in a half that is not uniform
 };
 
 // one compressed structure; all pointers address 32-bit words of one arena
@@ -59,7 +60,11 @@ struct PSpan {
   int kt0, kt1;   // template positions of the entries
   int q;          // repetition
   int kshift;     // position in the uncompressed arrays = template position + kshift
+  int qd, qd2;    // device spans: q * (uniform delta) of the two payloads, -1 when the region's deltas differ
 };
+
+// low half of a template entry (the value of repetition 0) read as a 16-bit load
+OCP_B200_HD int plow(const uint32_t* tent, int kt) { return reinterpret_cast<const uint16_t*>(tent)[2 * kt]; }
 
 // entries of outer index i
 OCP_B200_HD PSpan pspan(const PIndex& X, int i) {
@@ -74,6 +79,8 @@ OCP_B200_HD PSpan pspan(const PIndex& X, int i) {
   s.kt1 = static_cast<int>(X.tptr[t + 1]);
   s.q = q;
   s.kshift = R.koff + q * R.dk;
+  s.qd = (R.uni & 0xffff) ? q * ((R.uni & 0xffff) - 1) : -1;
+  s.qd2 = (R.uni >> 16) ? q * ((R.uni >> 16) - 1) : -1;
   return s;
 }
 OCP_B200_HD int pvalue(uint32_t ent, int q) { return static_cast<int>(ent & 0xffffu) + q * static_cast<int>(ent >> 16); }
@@ -117,7 +124,7 @@ __device__ __forceinline__ const PRegion* pregion(const PIndexDev& C, const uint
 }
 __device__ __forceinline__ PSpan pspan_dev(const PIndexDev& C, const uint32_t* ar, int i) {
   const PRegion* R = pregion(C, ar, C.ibound, i);
-  const int i0 = R->i0, i1 = R->i1, period = R->period, t0 = R->t0, koff = R->koff, dk = R->dk;
+  const int i0 = R->i0, i1 = R->i1, period = R->period, t0 = R->t0, koff = R->koff, dk = R->dk, uni = R->uni;
   const float inv = R->inv_period;
   const int o = i - i0;
   const int q = period < i1 - i0 ? static_cast<int>((static_cast<float>(o) + 0.5f) * inv) : 0;
@@ -127,6 +134,8 @@ __device__ __forceinline__ PSpan pspan_dev(const PIndexDev& C, const uint32_t* a
   s.kt1 = static_cast<int>(tp[1]);
   s.q = q;
   s.kshift = koff + q * dk;
+  s.qd = (uni & 0xffff) ? q * ((uni & 0xffff) - 1) : -1;
+  s.qd2 = (uni >> 16) ? q * ((uni >> 16) - 1) : -1;
   return s;
 }
 __device__ __forceinline__ int pvalue_at_dev(const PIndexDev& C, const uint32_t* ar, int k) {
@@ -235,19 +244,25 @@ inline bool build_periodic_index(const std::vector<int>& ptr, const std::vector<
     R.koff = R.k0 - R.kt0;
     R.inv_period = c.period > 0 ? 1.0f / static_cast<float>(c.period) : 0.0f;
     R.inv_dk = R.dk > 0 ? 1.0f / static_cast<float>(R.dk) : 0.0f;
+    int ud = -2, ud2 = -2;   // common delta of the region's entries: -2 none seen yet, -1 not uniform
     for (int o = 0; o < c.period; ++o) {
       out.tptr.push_back(static_cast<uint32_t>(out.tent.size()));
       for (int k = ptr[c.i0 + o]; k < ptr[c.i0 + o + 1]; ++k) {
         const int d = c.reps > 1 ? val[k + R.dk] - val[k] : 0;
         if (val[k] < 0 || val[k] >= 65536) return false;
         out.tent.push_back(static_cast<uint32_t>(val[k]) | (static_cast<uint32_t>(d) << 16));
+        ud = ud == -2 ? d : (ud == d ? ud : -1);
         if (two) {
           const int d2 = c.reps > 1 ? val2[k + R.dk] - val2[k] : 0;
           if (val2[k] < 0 || val2[k] >= 65536) return false;
           out.tent2.push_back(static_cast<uint32_t>(val2[k]) | (static_cast<uint32_t>(d2) << 16));
+          ud2 = ud2 == -2 ? d2 : (ud2 == d2 ? ud2 : -1);
         }
       }
     }
+    if (ud == -2) ud = 0;
+    if (ud2 == -2) ud2 = 0;
+    R.uni = ((ud >= 0 && ud < 65535) ? ud + 1 : 0) | (((ud2 >= 0 && ud2 < 65535) ? ud2 + 1 : 0) << 16);
     out.reg.push_back(R);
   }
   out.tptr.push_back(static_cast<uint32_t>(out.tent.size()));   // one shared end pointer: slots are consecutive
@@ -257,6 +272,8 @@ inline bool build_periodic_index(const std::vector<int>& ptr, const std::vector<
     const PSpan s = pspan(X, o);
     if (s.kt1 - s.kt0 != ptr[o + 1] - ptr[o] || s.kt0 + s.kshift != ptr[o]) return false;
     for (int kt = s.kt0; kt < s.kt1; ++kt) {
+      if (s.qd >= 0 && plow(X.tent, kt) + s.qd != val[kt + s.kshift]) return false;
+      if (two && s.qd2 >= 0 && plow(X.tent2, kt) + s.qd2 != val2[kt + s.kshift]) return false;
       if (pvalue(X.tent[kt], s.q) != val[kt + s.kshift]) return false;
       if (two && pvalue(X.tent2[kt], s.q) != val2[kt + s.kshift]) return false;
       if (pvalue_at(X, kt + s.kshift) != val[kt + s.kshift]) return false;
