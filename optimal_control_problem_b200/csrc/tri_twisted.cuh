@@ -395,8 +395,9 @@ __device__ inline void tri_solve_twisted(const PatternDev& P, const Work& W) {
   }
   __syncthreads();
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_FWD);
-  // border: y_p = b_p - sum_k L_pk y_k  (half a warp per border row, loads issued in batches of 8
-  // so that a slab-resident L_p costs one L2 latency per batch), x_p = D_p^-1 y_p
+  // border: y_p = b_p - sum_k L_pk y_k, x_p = D_p^-1 y_p.  Twelve border rows (a 12-state reference): whole warps
+  // per row, every load before the first FMA (border_rows_warp); otherwise half a warp per border row, loads
+  // issued in batches of 8 so that a slab-resident L_p costs one L2 latency per batch
   if (np > 0) {
     if (border_rows_by_warp(np, N, nw)) {
       border_rows_dispatch(W.Lp, bx, W.b, W.xp, N, warp, lane, nw);
