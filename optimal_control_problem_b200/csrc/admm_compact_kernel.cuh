@@ -420,7 +420,7 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
   OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_SOLVE_BWD);
 }
 
-template <int BS>
+template <int BS, bool kTile>   // kTile: chain steps of the factorisation in 2 x 2 tiles (thread groups of 64)
 __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, const ocp_b200_settings& S, const SolveArgs& A,
                                       Work& W, const Ctx& X, Reducer& R, int inst, QpResult& out, uint32_t tmem) {
   const int tid = threadIdx.x, T = blockDim.x;
@@ -557,7 +557,7 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
   clk.lap(OCP_B200_PHASE_SCALE);
   direct::tri_assemble_program(P, W, rv, sigma);
   clk.lap(OCP_B200_PHASE_KKT_ASSEMBLE);
-  direct::tri_factor_twisted<BS, true>(P, W);   // scratch: the iteration vectors (nothing lives there yet)
+  direct::tri_factor_twisted<BS, true, kTile>(P, W);   // scratch: the iteration vectors (nothing lives there yet)
   if constexpr (BS == 16) tmem_publish<BS>(W, P.tri_nb, tmem);
   clk.lap(OCP_B200_PHASE_FACTOR);
   // ---- cold start ----
@@ -767,7 +767,7 @@ __device__ inline void solve_instance(const PatternDev& P, const CompactIdx& C, 
         // (inlined a second time on purpose: an out-of-line copy shared with the set-up was measured slower,
         // 9.6 -> 9.8 ms per launch with P and W passed by value, 11.7 ms by reference)
         direct::tri_assemble_program(P, W, rv, sigma);
-        direct::tri_factor_twisted<BS, true>(P, W);
+        direct::tri_factor_twisted<BS, true, kTile>(P, W);
         if constexpr (BS == 16) tmem_publish<BS>(W, P.tri_nb, tmem);
         for (int j = tid; j < n; j += T) W.x[j] = X.sx[j];
         for (int i = tid; i < m; i += T) {
@@ -844,7 +844,10 @@ admm_compact_kernel(const PatternDev P, const CompactIdx C, const ocp_b200_setti
     __syncthreads();
     if (inst >= A.B) break;
     QpResult res;
-    solve_instance<BS>(P, C, S, A, W, X, R, inst, res, tmem);
+#ifndef OCP_B200_NO_TILE
+#define OCP_B200_NO_TILE 0   // 1: chain steps with one dot product at a time (A/B measurements)
+#endif
+    solve_instance<BS, kThreads == 128 && !OCP_B200_NO_TILE>(P, C, S, A, W, X, R, inst, res, tmem);
     write_outputs(P, A, W.x, W.y, R, inst, res);
   }
   if constexpr (BS == 16) {

@@ -28,7 +28,9 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 // kStaged: the caller guarantees stage != nullptr and F != nullptr (the compact kernel): without the run-time choice
 // between a global and a shared-memory operand the compiler keeps the address space of both and the dot products
 // load with LDS instead of generic loads.
-template <int BS, bool kTop, bool kStaged = false>
+// kTile: the dot products as 2 x 2 tiles (tri_fast.cuh: same bits, a third of the shared-memory loads) -- for thread
+// groups of at most BS * BS / 4 threads, where every thread has at least four results per loop anyway.
+template <int BS, bool kTop, bool kStaged = false, bool kTile = false>
 __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*ld*/, int k, int pred, int slot, double* S,
                                            double* Sp, double* Dpacc, int gt, int GT, int bar, double* stage, double* F = nullptr) {
   constexpr int bb = BS * BS, ld = BS + 2;   // compile-time pitch: addresses fold into immediates
@@ -50,9 +52,23 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
     C = stage; Dm = stage + W.stage_stride;
   }
   // coupling block into S; V_pred into Sp
+  if constexpr (kTile) {
+    for (int e = gt; e < bb / 4; e += GT) {
+      const int r0 = 2 * (e / (BS / 2)), c0 = 2 * (e % (BS / 2));
+      double o[4];
+      if (kTop) {
+        tile_cc<BS>(C + r0 * ld, C + (r0 + 1) * ld, Dm + c0 * ld, Dm + (c0 + 1) * ld, o);
+        S[r0 * ld + c0] = o[0]; S[r0 * ld + c0 + 1] = o[1]; S[(r0 + 1) * ld + c0] = o[2]; S[(r0 + 1) * ld + c0 + 1] = o[3];
+      } else {   // o[2 i + j] = sum_t Dm[c0 + i][t] C[t][r0 + j] = S[r0 + j][c0 + i]
+        tile_cs<BS>(Dm + c0 * ld, Dm + (c0 + 1) * ld, C + r0, ld, o);
+        S[r0 * ld + c0] = o[0]; S[(r0 + 1) * ld + c0] = o[1]; S[r0 * ld + c0 + 1] = o[2]; S[(r0 + 1) * ld + c0 + 1] = o[3];
+      }
+    }
+  } else {
   for (int e = gt; e < bb; e += GT) {
     const int r = e / BS, c = e % BS;
     S[r * ld + c] = kTop ? dot_cc<BS>(C + r * ld, Dm + c * ld) : dot_cs<BS>(Dm + c * ld, C + r, ld);
+  }
   }
   for (int e = gt; e < pb; e += GT) {
     const int r = e / BS, c = e % BS;
@@ -60,10 +76,38 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
   }
   group_barrier(bar, GT);
   // D_k -= coupling * K_{pred,k};  V_k -= V_pred coupling';  L_p,pred = V_pred D_pred^-1
+  const bool tile_p = kTile && (np & 1) == 0;   // border loops in tiles: even border size
+  if constexpr (kTile) {
+    for (int e = gt; e < bb / 4; e += GT) {
+      const int r0 = 2 * (e / (BS / 2)), c0 = 2 * (e % (BS / 2));
+      double o[4];
+      if (kTop) tile_cc<BS>(S + r0 * ld, S + (r0 + 1) * ld, C + c0 * ld, C + (c0 + 1) * ld, o);
+      else tile_cs<BS>(S + r0 * ld, S + (r0 + 1) * ld, C + c0, ld, o);
+      Dk[r0 * ld + c0] -= o[0]; Dk[r0 * ld + c0 + 1] -= o[1]; Dk[(r0 + 1) * ld + c0] -= o[2]; Dk[(r0 + 1) * ld + c0 + 1] -= o[3];
+    }
+  } else {
   for (int e = gt; e < bb; e += GT) {
     const int r = e / BS, c = e % BS;
     Dk[r * ld + c] -= kTop ? dot_cc<BS>(S + r * ld, C + c * ld) : dot_cs<BS>(S + r * ld, C + c, ld);
   }
+  }
+  if (tile_p) {
+    for (int e = gt; e < pb / 4; e += GT) {
+      const int r0 = 2 * (e / (BS / 2)), c0 = 2 * (e % (BS / 2));
+      double so[4], fo[4];
+      tile_cc<BS>(Sp + r0 * BS, Sp + (r0 + 1) * BS, S + c0 * ld, S + (c0 + 1) * ld, so);
+      tile_cc<BS>(Sp + r0 * BS, Sp + (r0 + 1) * BS, Dm + c0 * ld, Dm + (c0 + 1) * ld, fo);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int r = r0 + i, c = c0 + j;
+          W.Lp[size_t(r) * N + k * BS + c] -= so[2 * i + j];
+          W.Lp[size_t(r) * N + pred * BS + c] = fo[2 * i + j];
+          if (kStaged || F != nullptr) F[r * BS + c] = fo[2 * i + j];
+        }
+    }
+  } else {
   for (int e = gt; e < pb; e += GT) {
     const int r = e / BS, c = e % BS;
     const double s = dot_cc<BS>(Sp + r * BS, S + c * ld);
@@ -72,12 +116,24 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
     W.Lp[size_t(r) * N + pred * BS + c] = f;
     if (kStaged || F != nullptr) F[e] = f;   // shared-memory copy of L_p,pred for the accumulation below (L_p may live in the slab)
   }
+  }
   group_barrier(bar, GT);
   // D_p accumulator += V_pred L_p,pred';  slot <- coupling
+  if (tile_p && (kStaged || F != nullptr)) {
+    const int hp = np / 2;
+    for (int e = gt; e < hp * hp; e += GT) {
+      const int r0 = 2 * (e / hp), c0 = 2 * (e - (e / hp) * hp);
+      double o[4];
+      tile_cc<BS>(Sp + r0 * BS, Sp + (r0 + 1) * BS, F + c0 * BS, F + (c0 + 1) * BS, o);
+      Dpacc[r0 * (np + 1) + c0] += o[0]; Dpacc[r0 * (np + 1) + c0 + 1] += o[1];
+      Dpacc[(r0 + 1) * (np + 1) + c0] += o[2]; Dpacc[(r0 + 1) * (np + 1) + c0 + 1] += o[3];
+    }
+  } else {
   for (int e = gt; e < np * np; e += GT) {
     const int r = e / np, c = e - r * np;
     Dpacc[r * (np + 1) + c] += (kStaged || F != nullptr) ? dot_cc<BS>(Sp + r * BS, F + c * BS)
                                             : dot_cs<BS>(Sp + r * BS, W.Lp + size_t(c) * N + pred * BS, 1);
+  }
   }
   for (int e = gt; e < bb; e += GT) {
     const int r = e / BS, c = e % BS;
@@ -86,7 +142,7 @@ __device__ __forceinline__ void chain_step(const Work& W, int np, int N, int /*l
   group_barrier(bar, GT);
 }
 
-template <int BS, bool kStaged = false>
+template <int BS, bool kStaged = false, bool kTile = false>
 __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   const int np = P.tri_np, nb = P.tri_nb, N = nb * BS;
@@ -108,14 +164,14 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(1, GT);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_INVERT);
-      chain_step<BS, true, kStaged>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage, F);
+      chain_step<BS, true, kStaged, kTile>(W, np, N, ld, k + 1, k, k + 1, S, Sp, Dpacc, gt, GT, 1, stage, F);
       OCP_B200_FINE_LAP(clk, OCP_B200_PHASE_FACTOR_STEP);
     }
   } else {
     for (int k = nb - 1; k > mid + 1; --k) {  // blocks nb-1..mid+2; step into k-1 (>= mid+1)
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(k) * BS * ld, ld, lane, piv);
       group_barrier(2, GT);
-      chain_step<BS, false, kStaged>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage, F);
+      chain_step<BS, false, kStaged, kTile>(W, np, N, ld, k - 1, k, k, S, Sp, Dpacc, gt, GT, 2, stage, F);
     }
     if (mid + 1 < nb) {                       // block mid+1: inverted here, eliminated into mid below
       if (gt < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid + 1) * BS * ld, ld, lane, piv);
@@ -124,7 +180,7 @@ __device__ inline void tri_factor_twisted(const PatternDev& P, const Work& W) {
   }
   __syncthreads();
   // the bottom chain's last step lands on block mid as well: run it with the whole CTA
-  if (mid + 1 < nb) chain_step<BS, false, kStaged>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage, W.Fb);
+  if (mid + 1 < nb) chain_step<BS, false, kStaged, kTile>(W, np, N, ld, mid, mid + 1, mid + 1, W.S, W.Sp, W.Dp2, tid, T, 0, W.stage, W.Fb);
   if (tid < 32) warp_invert_exact<BS>(W.Dinv + size_t(mid) * BS * ld, ld, lane, W.piv);
   __syncthreads();
   // border of the last block, then D_p = K_pp - (accumulated) - V_mid L_p,mid', inverted
