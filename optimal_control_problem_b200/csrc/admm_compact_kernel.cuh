@@ -289,15 +289,10 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
   double* bx = W.b + np;
   OCP_B200_FINE_CLOCK(clk, W.phase);
   const uint32_t base = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
-  // the warps that idle during the forward sweep fetch their D_k^-1 row of the first diagonal pass now
-  const int dTb = (T / BS) * BS;
-  const bool pre = warp >= 2 && tid < dTb && tid < N;
-  double drow[BS];
-  if (pre) {
-    const double2* p2 = reinterpret_cast<const double2*>(W.Dinv + size_t(tid / BS) * BS * ld + (tid % BS) * ld);
-#pragma unroll
-    for (int i = 0; i < BS / 2; ++i) { const double2 v = p2[i]; drow[2 * i] = v.x; drow[2 * i + 1] = v.y; }
-  }
+  // (No prefetch of D_k^-1 rows by the warps that idle during the forward sweep, as direct::tri_solve_twisted does:
+  // here warps 0 and 1 run the sweep and load their rows in the diagonal phase anyway, so the pass is not shorter,
+  // and the 32 registers held across the sweep and the border phase cost 256 bytes of spills that the whole
+  // iteration loop paid for -- 7.75 -> 7.30 ms per launch without it, profiles/README.md.)
   // forward: both chains at once (warps 0 and 1), then the second contribution to block mid; the block row of that
   // joining slot is requested from the slab before warp 0 starts its chain
   double Lj[8];
@@ -362,16 +357,7 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
         const int j = tid < Tb ? base_j + tid : N;
         double v = 0.0;
         if (j < N) {
-          if (pre && base_j == 0) {
-            const double* yk = bx + k * BS;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-            for (int t = 0; t < BS; t += 4) {
-              s0 = fma(drow[t], yk[t], s0); s1 = fma(drow[t + 1], yk[t + 1], s1);
-              s2 = fma(drow[t + 2], yk[t + 2], s2); s3 = fma(drow[t + 3], yk[t + 3], s3);
-            }
-            v = (s0 + s1) + (s2 + s3);
-          } else {
+          {
             const double2* d2 = reinterpret_cast<const double2*>(W.Dinv + size_t(k) * BS * ld + r1 * ld);
             const double* yk = bx + k * BS;
             double dr[BS];
