@@ -293,11 +293,12 @@ __device__ inline void tri_solve_twisted_tmem(const PatternDev& P, const Work& W
   // here warps 0 and 1 run the sweep and load their rows in the diagonal phase anyway, so the pass is not shorter,
   // and the 32 registers held across the sweep and the border phase cost 256 bytes of spills that the whole
   // iteration loop paid for -- 7.75 -> 7.30 ms per launch without it, profiles/README.md.)
-  // forward: both chains at once (warps 0 and 1), then the second contribution to block mid; the block row of that
-  // joining slot is requested from the slab before warp 0 starts its chain
+  // forward: both chains at once (warps 0 and 1), then the second contribution to block mid
+  // (the block row of the joining slot is requested AFTER warp 0's chain: requested before it, its eight doubles sit
+  // in registers through the whole chain -- 7.29 -> 7.08 ms per launch for the later load, profiles/README.md)
   double Lj[8];
-  if (warp == 0 && mid + 1 < nb) slab_block_part<BS, false>(W.Lsub, mid + 1, lane, Lj);
   if (warp < 2) run_chain_tmem<BS, false>(W, bx, sweep_chain(warp, nb), base, lane);
+  if (warp == 0 && mid + 1 < nb) slab_block_part<BS, false>(W.Lsub, mid + 1, lane, Lj);
   __syncthreads();
   if (warp == 0 && mid + 1 < nb) direct::sweep_stage<BS>(Lj, bx + (mid + 1) * BS + (lane & 1) * 8, bx + mid * BS + (lane >> 1), (lane & 1) == 0);
   __syncthreads();
