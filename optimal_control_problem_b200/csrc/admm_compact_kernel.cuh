@@ -254,23 +254,42 @@ __device__ __forceinline__ void run_chain_tmem(const Work& W, double* bx, const 
   const int row = lane >> 1, half = lane & 1;
   const bool writer = half == 0;
   const int ntm = ch.count < kTmemBlocks ? ch.count : kTmemBlocks;
+#ifndef OCP_B200_CHAIN_PREFETCH
+#define OCP_B200_CHAIN_PREFETCH 1   // 3: three slab stages requested when the sweep starts (the first Tensor-Memory version)
+#endif
+#if OCP_B200_CHAIN_PREFETCH == 3
   const int nreg = ch.count - ntm < 3 ? ch.count - ntm : 3;
   double Ra[CPL], Rb[CPL], Rc[CPL];
   if (nreg > 0) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + ntm * ch.dslot, lane, Ra);
   if (nreg > 1) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + (ntm + 1) * ch.dslot, lane, Rb);
   if (nreg > 2) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + (ntm + 2) * ch.dslot, lane, Rc);
+#else
+  // one slab stage behind the Tensor-Memory ones, requested four stages before it is needed (an L2 latency): every
+  // register held through the chain is paid for by the whole iteration loop
+  const int nreg = ch.count > ntm ? 1 : 0;
+  const int ireq = ntm > 4 ? ntm - 4 : 0;
+  double Ra[CPL];
+#endif
   const int db = ch.dblk * BS;
   const double* srcp = bx + ch.src0 * BS + half * CPL;
   double* dstp = bx + ch.dst0 * BS + row;
   for (int i = 0; i < ntm; ++i) {
+#if OCP_B200_CHAIN_PREFETCH != 3
+    if (nreg > 0 && i == ireq) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + ntm * ch.dslot, lane, Ra);
+#endif
     double L[CPL];
     tmem_ld16(base + 16 * i, L);
     direct::sweep_stage<BS>(L, srcp, dstp, writer);
     srcp += db; dstp += db;
   }
+#if OCP_B200_CHAIN_PREFETCH != 3
+  if (nreg > 0 && ntm == 0) slab_block_part<BS, kColumn>(W.Lsub, ch.slot0, lane, Ra);
+#endif
   if (nreg > 0) { direct::sweep_stage<BS>(Ra, srcp, dstp, writer); srcp += db; dstp += db; }
+#if OCP_B200_CHAIN_PREFETCH == 3
   if (nreg > 1) { direct::sweep_stage<BS>(Rb, srcp, dstp, writer); srcp += db; dstp += db; }
   if (nreg > 2) { direct::sweep_stage<BS>(Rc, srcp, dstp, writer); srcp += db; dstp += db; }
+#endif
   for (int i = ntm + nreg; i < ch.count; ++i) {
     double L[CPL];
     slab_block_part<BS, kColumn>(W.Lsub, ch.slot0 + i * ch.dslot, lane, L);
